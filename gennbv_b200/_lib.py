@@ -1,0 +1,55 @@
+"""ctypes binding of libgennbv_b200.so (the C ABI declared in include/gennbv_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgennbv_b200.so")
+ABI_VERSION = 1
+
+_lib = None
+
+c_void_p, c_int, c_int64, c_size_t, c_uint32, c_double, c_float = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_double, ctypes.c_float)
+
+# name -> (restype, argtypes); mirrors include/gennbv_b200.h one to one
+SIGNATURES = {
+    "gnbv_abi_version": (c_int, []),
+    "gnbv_last_error": (ctypes.c_char_p, []),
+    "gnbv_voxelize_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "gnbv_voxelize_step": (c_int, [c_void_p] * 11 + [c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                                      c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "gnbv_scan_raycast": (c_int, [c_void_p] * 9 + [c_size_t, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
+    "gnbv_grid_update": (c_int, [c_void_p] * 4 + [c_int64, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "gnbv_voxelize_masks": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
+                                    ctypes.POINTER(c_int64)]),
+    "gnbv_reset_grids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "gnbv_gae": (c_int, [c_void_p] * 5 + [c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def lib():
+    """The loaded library; raises if it has not been built (python -m gennbv_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: gennbv_b200 has no CPU fallback. Build it with "
+                "`python -m gennbv_b200.build` (nvcc, sm_100a).")
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)          # AttributeError if the export is missing
+            fn.restype, fn.argtypes = res, args
+        got = h.gnbv_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"libgennbv_b200.so ABI {got} != binding ABI {ABI_VERSION}: rebuild")
+        _lib = h
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().gnbv_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

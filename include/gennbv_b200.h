@@ -1,0 +1,112 @@
+/* gennbv_b200.h -- C ABI of the B200-native GenNBV hot path (libgennbv_b200.so).
+ *
+ * The reference (zjwzcx/GenNBV @ c373f76) has no FFI layer: its seams are Python call
+ * signatures.  Each entry point below names the reference lines it
+ * replaces; gennbv_b200/*.py keeps the reference's Python names on top of these and
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless marked "host";
+ *     the caller owns all memory, the library never allocates and never synchronises;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - tensors are dense, row-major, in the reference's own dtypes and layouts;
+ *   - return value 0 = OK, <0 = error (GNBV_E_*); gnbv_last_error() returns a
+ *     thread-local, human-readable message for the last failing call.
+ */
+#ifndef GENNBV_B200_H
+#define GENNBV_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNBV_OK 0
+#define GNBV_E_ARG (-1)      /* bad argument (null pointer, unsupported size, misalignment) */
+#define GNBV_E_CUDA (-2)     /* a CUDA runtime call / kernel launch failed */
+#define GNBV_E_WORKSPACE (-3) /* workspace too small */
+
+#define GNBV_ABI_VERSION 1
+
+int gnbv_abi_version(void);
+const char* gnbv_last_error(void);
+
+/* ---- flags for gnbv_voxelize_step ---- */
+#define GNBV_RAW_DEPTH 1u   /* depth is the raw sensor image: apply post_process_camera_tensor's chain first */
+
+/* Workspace for gnbv_voxelize_step (bytes): two occupancy bit-masks + coverage partial sums. */
+size_t gnbv_voxelize_workspace_bytes(int num_envs, int grid_size);
+
+/* One env.step() worth of state encoding for all N envs, three launches, no host sync.
+ * Replaces (per step, for all envs at once):
+ *   Env_Train_Base.post_process_camera_tensor   gennbv/env/env_train_base.py:519-523  (depth chain; GNBV_RAW_DEPTH)
+ *   Env_Train_GenNBV.back_projection_fg         gennbv/env/env_train_gennbv.py:494-533
+ *   scanned_pts_to_idx_3D                       gennbv/utils.py:230-270
+ *   pose_coord_to_idx_3D                        gennbv/utils.py:273-306
+ *   bresenham3D_pycuda                          gennbv/utils.py:24-227
+ *   Env_Train_GenNBV.update_occ_grid            gennbv/env/env_train_gennbv.py:277-326
+ *   grid_occupancy_tri_cls                      gennbv/utils.py:309-325
+ *   the sum in _reward_surface_coverage         gennbv/env/env_train_gennbv.py:537
+ *
+ *   depth      [N,H,W] f32   processed depth, or raw sensor depth with GNBV_RAW_DEPTH
+ *   seg        [N,H,W] i32   segmentation ids (foreground = seg > 50)
+ *   kinv       [3,3]   f32   inverse intrinsics
+ *   c2w        [N,4,4] f32   camera-to-world, env-local (env origin already subtracted)
+ *   range_gt   [N,6]   f32   x_max,x_min,y_max,y_min,z_max,z_min
+ *   voxel_size [N,3]   f32
+ *   pose_xyz   [N,3]   f32   camera position (ray source)
+ *   grid_gt    [N,G,G,G] f32 GT occupancy {0,1}
+ *   prob_grid  [N,G,G,G] f32 in/out
+ *   scanned_gt [N,G,G,G] f32 in/out
+ *   tri_out    f32 out: row n starts at tri_out + n*tri_row_stride (elements), G^3 values in {-1,0,1};
+ *              tri_row_stride = G^3 for a dense [N,G,G,G] tensor, or the flattened observation row
+ *              length when writing straight into the obs buffer (env_wrapper_gennbv_train.py:27-56)
+ *   cov_sum    [N] f32 out   sum of scanned_gt per env after the update
+ *   num_targets[N] i32 out   number of distinct occupied voxels hit this step (may be NULL)
+ */
+int gnbv_voxelize_step(const float* depth, const int32_t* seg, const float* kinv, const float* c2w,
+                       const float* range_gt, const float* voxel_size, const float* pose_xyz,
+                       const float* grid_gt, float* prob_grid, float* scanned_gt,
+                       float* tri_out, int64_t tri_row_stride, float* cov_sum, int32_t* num_targets,
+                       void* workspace, size_t workspace_bytes,
+                       int num_envs, int height, int width, int grid_size, uint32_t flags, void* stream);
+
+/* The two phases of gnbv_voxelize_step as separate entry points (same arguments, same workspace):
+ *   gnbv_scan_raycast : back_projection_fg + scanned_pts_to_idx_3D + pose_coord_to_idx_3D + bresenham3D_pycuda
+ *                       -> target / touched bit-masks in the workspace (see gnbv_voxelize_masks)
+ *   gnbv_grid_update  : the dense part of update_occ_grid (env_train_gennbv.py:311-326), grid_occupancy_tri_cls
+ *                       and the coverage sum, consuming those masks.
+ * gnbv_voxelize_step == gnbv_scan_raycast followed by gnbv_grid_update. */
+int gnbv_scan_raycast(const float* depth, const int32_t* seg, const float* kinv, const float* c2w,
+                      const float* range_gt, const float* voxel_size, const float* pose_xyz,
+                      int32_t* num_targets, void* workspace, size_t workspace_bytes,
+                      int num_envs, int height, int width, int grid_size, uint32_t flags, void* stream);
+int gnbv_grid_update(const float* grid_gt, float* prob_grid, float* scanned_gt,
+                     float* tri_out, int64_t tri_row_stride, float* cov_sum,
+                     void* workspace, size_t workspace_bytes, int num_envs, int grid_size, void* stream);
+
+/* Debug/compat view of the step's intermediate sets, valid after gnbv_voxelize_step on the same
+ * workspace: bit v of row n (v = (x*G+y)*G+z, little-endian within u32 words) of
+ *   target mask  = voxels returned by scanned_pts_to_idx_3D (+unique) for env n  (utils.py:230-270)
+ *   touched mask = union of bresenham3D_pycuda's in-bounds path voxels for env n  (utils.py:24-227)
+ * words_per_env receives the row pitch in u32 words. Returned pointers alias `workspace`. */
+int gnbv_voxelize_masks(void* workspace, int num_envs, int grid_size,
+                        const uint32_t** target_mask, const uint32_t** touched_mask, int64_t* words_per_env);
+
+/* reset_idx's grid part (env_train_gennbv.py:413-417): zero prob_grid / scanned_gt rows whose
+ * reset flag is non-zero.  reset_flags [N] u8 on device -- no host round trip. */
+int gnbv_reset_grids(float* prob_grid, float* scanned_gt, const uint8_t* reset_flags,
+                     int num_envs, int grid_size, void* stream);
+
+/* TensorRolloutBuffer_Grid_Obs.compute_returns_and_advantage  (stable_baselines3/common/buffers.py:706-724)
+ *   rewards, values [T,N] f32; episode_starts [T,N] u8; last_values [N] f32; dones [N] u8
+ *   advantages, returns [T,N] f32 out.  gamma / gae_lambda are the Python doubles of the buffer. */
+int gnbv_gae(const float* rewards, const float* values, const uint8_t* episode_starts,
+             const float* last_values, const uint8_t* dones, double gamma, double gae_lambda,
+             int n_steps, int num_envs, float* advantages, float* returns, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GENNBV_B200_H */

@@ -1,0 +1,129 @@
+"""TEST HARNESS ONLY -- writes tests/golden/*.npz from the reference's own Python.
+
+Run in the build container (needs /root/reference):   python oracle/gen_golden.py
+The fixtures are committed; the GPU box (no /root/reference) only reads them.
+
+env_*.npz : a roll-out of the reference's unmodified `Env_Train_GenNBV` on CPU
+    (oracle/ref_driver.py: Isaac Gym replaced by the synthetic renderer, PyCUDA Bresenham
+    replaced by the C restatement), recording for reset() and every step():
+      inputs : actions[T,N,6] i64 (as handed to step), raw sensor images depth[T+1,N,H,W] f32
+               (negative z-depth, -inf = no hit), seg[T+1,N,H,W] i32, rgb[T+1,N,H,W,4] u8,
+               view matrices [T+1,N,4,4] f32 (Isaac convention) and the c2w the reference
+               derives from them (env_train_gennbv.py:512-514)
+      outputs: prob_grid / scanned_gt_grid / tri grid after the step (i8 codes + the distinct
+               fp32 values, see `_pack_f32`), coverage ratio, rewards, dones, time_outs,
+               episode_length_buf, poses, the obs dict's "state" and "state_rgb".
+    index 0 of the [T+1] arrays is reset().
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _HERE)
+sys.path.insert(0, os.path.dirname(_HERE))
+
+import ref_driver  # noqa: E402
+from gennbv_b200 import synth  # noqa: E402
+
+GOLDEN_DIR = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+
+
+def _pack_f32(a):
+    """Grids hold a handful of distinct fp32 values: store the palette (as raw bits) + u8 codes."""
+    bits = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    pal, codes = np.unique(bits, return_inverse=True)
+    assert pal.size <= 256, pal.size
+    return pal, codes.reshape(a.shape).astype(np.uint8)
+
+
+def unpack_f32(pal, codes):
+    return pal[codes].view(np.float32)
+
+
+def rollout(name, N, H, W, G, S, T, max_episode_length, seed):
+    torch.manual_seed(seed)
+    scenes = synth.make_house_scenes(S, G, seed=seed)
+    env, ref = ref_driver.make_reference_env(N, H, W, scenes, buffer_size=100,
+                                             max_episode_length=max_episode_length)
+    gen = torch.Generator().manual_seed(seed + 1)
+    rec = {k: [] for k in ("depth", "seg", "rgb", "view", "c2w", "prob", "scan", "tri", "ratio", "rew", "done",
+                           "time_out", "ep_len", "poses", "state", "state_rgb", "rgb_gray", "applied_actions")}
+    actions = []
+
+    # reset_idx writes init_pose_buf through pose_buf[-1], which aliases env.poses (env_train_gennbv.py:268-270,
+    # 397-399) and overwrites env.actions (:409-411): record what the step actually used, before the reset
+    used = {}
+    inner_update = env.update_occ_grid
+
+    def update_occ_grid_spy():
+        used["poses"] = env.poses.numpy().copy()
+        used["actions"] = env.actions.numpy().copy()
+        inner_update()
+
+    env.update_occ_grid = update_occ_grid_spy
+
+    def snap(obs, rew, done):
+        rec["depth"].append(torch.stack(env.depth_cam_tensors).numpy().copy())
+        rec["seg"].append(torch.stack(env.seg_cam_tensors).numpy().copy())
+        rec["rgb"].append(torch.stack(env.rgb_cam_tensors).numpy().copy())
+        rec["view"].append(env._view_matrix.copy())
+        rec["c2w"].append(synth.c2w_from_view_matrix(torch.from_numpy(env._view_matrix), env.env_origins).numpy())
+        rec["prob"].append(env.prob_grid.numpy().copy())
+        rec["scan"].append(env.scanned_gt_grid.numpy().copy())
+        rec["tri"].append(obs["grid"].numpy().astype(np.int8))
+        rec["ratio"].append(env.reward_ratio_buf[-1].numpy().copy())
+        rec["rew"].append(rew.numpy().copy())
+        rec["done"].append(done.numpy().copy())
+        rec["time_out"].append(env.extras["time_outs"].numpy().copy())
+        rec["ep_len"].append(env.episode_length_buf.numpy().copy())
+        rec["poses"].append(used["poses"])
+        rec["state"].append(obs["state"].numpy().copy())
+        rec["state_rgb"].append(obs["state_rgb"].numpy().copy())
+        rec["rgb_gray"].append(env.rgb_grayscale.numpy().copy())
+        rec["applied_actions"].append(used["actions"])
+
+    obs = env.reset()
+    snap(obs, env.rew_buf, env.reset_buf.clone())
+    for t in range(T):
+        a = synth.sample_lookat_actions(scenes.params, N, gen)
+        if t % 3 == 2:      # some out-of-range requests to exercise the clip (env_train_gennbv.py:247)
+            a[0, 0], a[-1, 2], a[0, 4] = 95, -4, 20
+        actions.append(a.numpy().copy())
+        obs, rew, done, info = env.step(a)
+        snap(obs, rew, done)
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out["actions"] = np.stack(actions)
+    for k in ("prob", "scan"):
+        out[k + "_pal"], out[k + "_codes"] = _pack_f32(out.pop(k))
+    out["grid_gt_file"] = np.packbits(scenes.grid_gt[..., 3].numpy().astype(bool), axis=None)
+    out["grid_centres_lohi"] = np.stack([scenes.grid_gt[:, 0, 0, 0, :3].numpy(), scenes.grid_gt[:, -1, -1, -1, :3].numpy()], 1)
+    out["scene_params"] = scenes.params.numpy()
+    out["range_gt"] = env.range_gt.numpy()
+    out["voxel_size_gt"] = env.voxel_size_gt.numpy()
+    out["num_valid_voxel_gt"] = env.num_valid_voxel_gt.numpy()
+    out["env_origins"] = env.env_origins.numpy()
+    out["inv_intri"] = env.inv_intri.numpy()
+    out["reward_scales"] = np.array([env.reward_scales["surface_coverage"], env.reward_scales["short_path"],
+                                     env.reward_scales["termination"]], np.float64)
+    out["meta"] = np.array([N, H, W, G, S, T, max_episode_length, seed], np.int64)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{path}: {os.path.getsize(path) / 1e6:.2f} MB; dones={int(out['done'][1:].sum())} "
+          f"timeouts={int(out['time_out'][1:].sum())} final ratio={out['ratio'][-1]}")
+
+
+def main():
+    # reference-native grid (20^3), short episodes so time-outs / resets / forced init_action occur
+    rollout("env_g20", N=4, H=48, W=48, G=20, S=3, T=14, max_episode_length=5, seed=0)
+    # BASELINE config 1 shape: one env, 128x128 depth, 64^3 grid
+    rollout("env_g64", N=1, H=128, W=128, G=64, S=1, T=4, max_episode_length=100, seed=3)
+    # non-square image, longer episode (coverage saturates; `ratio > 0.99` termination if reached)
+    rollout("env_g20_long", N=3, H=40, W=56, G=20, S=2, T=40, max_episode_length=100, seed=5)
+
+
+if __name__ == "__main__":
+    main()
