@@ -26,6 +26,12 @@ SIGNATURES = {
     "gnbv_voxelize_masks": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                                     ctypes.POINTER(c_int64)]),
     "gnbv_reset_grids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "gnbv_actions_to_poses": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p]),
+    "gnbv_obs_update": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_int] * 8 + [c_void_p]),
+    "gnbv_episode_stats_doubles": (c_size_t, []),
+    "gnbv_reward_termination": (c_int, [c_void_p] * 14 + [c_double] * 3 + [c_int] * 3 + [c_int64, c_double, c_double,
+                                                                                       c_int, c_void_p]),
+    "gnbv_reset_envs": (c_int, [c_void_p] * 11 + [c_int] * 8 + [c_void_p]),
     "gnbv_gae": (c_int, [c_void_p] * 5 + [c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

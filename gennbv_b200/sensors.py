@@ -1,0 +1,60 @@
+"""Sensor sources: what Isaac Gym hands the reference env every step.
+
+In the reference, `gym.render_all_camera_sensors` refreshes per-env GPU image tensors (depth / segmentation /
+RGBA, env_train_gennbv.py:204-227,349-354) and `get_camera_view_matrix` returns the per-env view matrices as a
+host numpy array (env_train_base.py:777-785).  Isaac Gym is closed source and absent here, so the env takes an
+injectable source with the same outputs; `SyntheticHouseSensor` renders the analytic scenes of gennbv_b200.synth
+on the device, `ReplaySensor` replays recorded frames (used by the parity tests)."""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import synth
+
+
+@dataclass
+class SensorFrame:
+    depth: torch.Tensor                 # [N,H,W] f32 raw (negative z-depth, -inf = no hit), on the env's device
+    seg: torch.Tensor                   # [N,H,W] i32
+    rgba: Optional[torch.Tensor]        # [N,H,W,4] u8 or None
+    c2w: Optional[torch.Tensor] = None          # [N,4,4] f32 env-local camera-to-world on the device, or
+    view_matrix: Optional[np.ndarray] = None    # [N,4,4] f32 host array in Isaac's convention (one of the two)
+    contact: Optional[torch.Tensor] = None      # [N] u8 collision flags (None = no contacts)
+
+
+class SensorSource:
+    height: int
+    width: int
+
+    def render(self, poses: torch.Tensor) -> SensorFrame:      # poses [N,6] f32 (x,y,z,roll,pitch,yaw)
+        raise NotImplementedError
+
+
+class SyntheticHouseSensor(SensorSource):
+    """Analytic box+gable-roof scenes (gennbv_b200.synth), rendered on the device for the current poses."""
+
+    def __init__(self, scene_params, height, width, fov_deg=90.0, with_rgb=True, device="cuda"):
+        self.params = scene_params.to(device)
+        self.height, self.width, self.fov, self.with_rgb = height, width, fov_deg, with_rgb
+
+    def render(self, poses):
+        depth, seg, rgb, c2w = synth.render(self.params, poses, self.height, self.width, self.fov, with_rgb=self.with_rgb)
+        return SensorFrame(depth=depth.contiguous(), seg=seg.contiguous(), rgba=rgb, c2w=c2w.float().contiguous())
+
+
+class ReplaySensor(SensorSource):
+    """Replays recorded raw frames + Isaac-convention view matrices (host), ignoring the requested poses."""
+
+    def __init__(self, depth, seg, rgba, view_matrix, device):
+        self.depth, self.seg, self.rgba, self.view = depth, seg, rgba, view_matrix
+        self.height, self.width = depth.shape[-2:]
+        self.device, self.t = device, 0
+
+    def render(self, poses):
+        t = self.t
+        self.t += 1
+        d = lambda a: torch.from_numpy(np.ascontiguousarray(a[t])).to(self.device)
+        return SensorFrame(depth=d(self.depth), seg=d(self.seg), rgba=d(self.rgba) if self.rgba is not None else None,
+                           view_matrix=np.ascontiguousarray(self.view[t]))

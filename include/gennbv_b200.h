@@ -99,6 +99,54 @@ int gnbv_voxelize_masks(void* workspace, int num_envs, int grid_size,
 int gnbv_reset_grids(float* prob_grid, float* scanned_gt, const uint8_t* reset_flags,
                      int num_envs, int grid_size, void* stream);
 
+/* ---- env.step() bookkeeping: everything below runs for all envs on device, no host read-back ---- */
+
+/* Env_Train_GenNBV.step() head (env_train_gennbv.py:246-255 + env_train_base.py:665-667):
+ * actions_out = clip(actions_in, idx_low, idx_up); rows with episode_length == 0 are forced to init_action;
+ * poses = actions_out * unit + low_world (fp32).  actions [N,A] i64, poses [N,A] f32, per-axis vectors [A]. */
+int gnbv_actions_to_poses(const int64_t* actions_in, const int64_t* episode_length, const int64_t* idx_low,
+                          const int64_t* idx_up, const int64_t* init_action, const float* unit, const float* low_world,
+                          int64_t* actions_out, float* poses, int num_envs, int action_dim, void* stream);
+
+/* rgb part of post_process_camera_tensor (env_train_base.py:514-518: nearest resize to rgb_h x rgb_w, torchvision
+ * rgb_to_grayscale on uint8, .float()), update_obs_buf (env_train_gennbv.py:273-275: push pose and frame into the
+ * histories) and the "state" / "state_rgb" columns of the flattened observation (env_train_gennbv.py:359-366 +
+ * env_wrapper_gennbv_train.py:27-56).
+ *   rgba [N,H,W,4] u8 (NULL = black frame); poses [N,pose_dim] f32;
+ *   pose_hist [N,hist_len,pose_dim] f32 in/out (oldest first); rgb_hist [N,rgb_frames,rgb_h,rgb_w] f32 in/out;
+ *   obs row n starts at obs + n*obs_row_stride; state at +state_off, frames at +rgb_off (elements). */
+int gnbv_obs_update(const uint8_t* rgba, const float* poses, float* pose_hist, float* rgb_hist, float* obs,
+                    int64_t obs_row_stride, int64_t state_off, int64_t rgb_off, int num_envs, int height, int width,
+                    int hist_len, int pose_dim, int rgb_frames, int rgb_h, int rgb_w, void* stream);
+
+/* Number of doubles in the `stats` block of gnbv_reward_termination. Layout: [0] ring position, [1] ring count,
+ * [2,102) finished-episode rewards, [102,202) finished-episode lengths, [202] mean reward, [203] mean length,
+ * [204..206] rew_surface_coverage / rew_short_path / rew_termination (infos["episode"], env_train_gennbv.py:424-428). */
+size_t gnbv_episode_stats_doubles(void);
+
+/* post_physics_step's scalar part: episode_length += 1 (env_train_gennbv.py:336); compute_reward with
+ * _reward_surface_coverage, _reward_short_path, check_termination, _reward_termination
+ * (env_train_base.py:377-398; env_train_gennbv.py:438-457,535-556); update_extra_episode_info
+ * (env_train_base.py:629-639) and reset_idx's episode statistics (env_train_gennbv.py:424-436).
+ * All [N]; flags are u8 {0,1}; episode_sums [3,N] (coverage, short_path, termination); scales are the Python
+ * doubles reward_scales[name] (cfg scale x dt). collision may be NULL (no contacts).
+ * time_outs_extra reproduces infos["time_outs"], which the reference rebinds only inside reset_idx. */
+int gnbv_reward_termination(const float* cov_sum, const float* num_valid, float* ratio_prev, int64_t* episode_length,
+                            const uint8_t* collision, float* rew_buf, uint8_t* reset_buf, uint8_t* time_out_buf,
+                            uint8_t* dones_out, float* episode_sums, float* cur_reward_sum, float* cur_episode_length,
+                            double* stats, uint8_t* time_outs_extra, double scale_cov, double scale_short,
+                            double scale_term, int has_termination_reward, int only_positive_rewards, int max_step_done,
+                            int64_t max_episode_length, double max_episode_length_s, double ratio_threshold,
+                            int num_envs, void* stream);
+
+/* reset_idx's buffer resets for rows with reset_buf != 0 (env_train_gennbv.py:395-421): grids zeroed, pose history
+ * <- init_pose, frames <- 0, ratio <- 0, actions <- init_action, episode_length <- 0, episode_sums <- 0;
+ * clear_reset_buf != 0 then zeroes reset_buf (env_train_gennbv.py:373). */
+int gnbv_reset_envs(uint8_t* reset_buf, float* prob_grid, float* scanned_gt, float* pose_hist, float* rgb_hist,
+                    float* ratio_prev, int64_t* actions, int64_t* episode_length, float* episode_sums,
+                    const float* init_pose, const int64_t* init_action, int num_envs, int grid_size, int hist_len,
+                    int pose_dim, int rgb_frames, int rgb_h, int rgb_w, int clear_reset_buf, void* stream);
+
 /* TensorRolloutBuffer_Grid_Obs.compute_returns_and_advantage  (stable_baselines3/common/buffers.py:706-724)
  *   rewards, values [T,N] f32; episode_starts [T,N] u8; last_values [N] f32; dones [N] u8
  *   advantages, returns [T,N] f32 out.  gamma / gae_lambda are the Python doubles of the buffer. */
