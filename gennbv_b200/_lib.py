@@ -11,8 +11,25 @@ ABI_VERSION = 1
 
 _lib = None
 
-c_void_p, c_int, c_int64, c_size_t, c_uint32, c_double, c_float = (
-    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_double, ctypes.c_float)
+c_void_p, c_int, c_int64, c_size_t, c_uint32, c_double, c_float, c_uint64 = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_double, ctypes.c_float,
+    ctypes.c_uint64)
+
+
+class EncoderParams(ctypes.Structure):
+    """gnbv_encoder_params (include/gennbv_b200.h): 24 device pointers in declaration order."""
+    FIELDS = ["conv1_w", "conv1_b", "bn1_w", "bn1_b", "bn1_rm", "bn1_rv", "bn1_nbt",
+              "conv2_w", "conv2_b", "bn2_w", "bn2_b", "bn2_rm", "bn2_rv", "bn2_nbt",
+              "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b"]
+    _fields_ = [(f, ctypes.c_void_p) for f in FIELDS]
+
+
+class EncoderGrads(ctypes.Structure):
+    """gnbv_encoder_grads: 16 device pointers in declaration order (== Hybrid_Encoder._param_list())."""
+    FIELDS = ["conv1_w", "conv1_b", "bn1_w", "bn1_b", "conv2_w", "conv2_b", "bn2_w", "bn2_b",
+              "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b"]
+    _fields_ = [(f, ctypes.c_void_p) for f in FIELDS]
+
 
 # name -> (restype, argtypes); mirrors include/gennbv_b200.h one to one
 SIGNATURES = {
@@ -32,6 +49,25 @@ SIGNATURES = {
     "gnbv_reward_termination": (c_int, [c_void_p] * 14 + [c_double] * 3 + [c_int] * 3 + [c_int64, c_double, c_double,
                                                                                        c_int, c_void_p]),
     "gnbv_reset_envs": (c_int, [c_void_p] * 11 + [c_int] * 8 + [c_void_p]),
+    "gnbv_encoder_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gnbv_encoder_forward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnbv_encoder_backward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_void_p]),
+    "gnbv_policy_heads_forward": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "gnbv_multicategorical_evaluate": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_int), c_int, c_void_p, c_void_p,
+                                               c_void_p, c_int, c_void_p]),
+    "gnbv_multicategorical_sample": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_int), c_int, c_uint64, c_uint64, c_int,
+                                             c_void_p, c_void_p, c_int, c_void_p]),
+    "gnbv_multicategorical_backward": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_int), c_int, c_void_p, c_void_p,
+                                               c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "gnbv_ppo_loss": (c_int, [c_void_p] * 7 + [c_int] + [c_double] * 5 + [c_int] + [c_void_p] * 5),
+    "gnbv_clip_adam_workspace_bytes": (c_size_t, []),
+    "gnbv_grad_norm": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p]),
+    "gnbv_adam_step": (c_int, [c_void_p] * 4 + [c_int64, c_void_p] + [c_double] * 4 + [c_int64, c_double, c_void_p]),
+    "gnbv_sgemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gnbv_sgemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                           c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "gnbv_gae": (c_int, [c_void_p] * 5 + [c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

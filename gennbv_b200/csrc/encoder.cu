@@ -1,0 +1,890 @@
+// encoder.cu -- Hybrid_Encoder (gennbv/network/hybrid_encoder.py:12-91) + actor / critic heads
+// (stable_baselines3/common/policies.py:954-1090) forward and backward, hand-written for sm_100a.
+//
+// Layout decisions (B200-first, not a translation of the cuDNN/cuBLAS call sequence):
+//   * the observation row is consumed in place: `state` columns feed the positional encoding, the tri-class grid
+//     columns feed conv1 directly (no reshape / slice copies), the rgb columns are never read (the reference's
+//     forward ignores them, hybrid_encoder.py:69-91);
+//   * conv1 (Cin = 1, 27 taps) is a register-resident stencil, one thread per output voxel x 16 channels,
+//     output kept channels-last (NDHWC) so that conv2 reads 64 B per voxel with 128-bit loads;
+//   * BatchNorm3d + ReLU are never materialised for layer 1: conv2 applies a*y+b / max on load; batch statistics
+//     are reduced from per-block (sum, sum of squares) partials in double in a fixed order (deterministic);
+//   * conv2 (K = 432, N = 16) is an implicit GEMM on CUDA cores: 4 output voxels x 16 channels per thread,
+//     weights broadcast from shared memory with LDS.128 (1 shared load per 16 FMA);
+//   * Linear layers use the fp32 split-K GEMM of gemm.cu (fp32 everywhere: the 1e-4 parity budget rules out
+//     bf16 / tf32 operands, see gemm.cuh).
+#include "gemm.cuh"
+
+#include <algorithm>
+
+namespace gnbv {
+
+constexpr int C1 = 16;            // conv channels (hybrid_encoder.py:32,35)
+constexpr int TAPS = 27;
+constexpr int CONV1_THREADS = 256;
+constexpr int CONV2_THREADS = 128;
+constexpr int CONV2_ZT = 4;       // output voxels (along z) per thread
+
+
+constexpr int PART_STRIDE = 2 * C1 + 4;      // per block: mean[16], M2[16], count, pad
+
+// Block-level (count, mean, M2) of `nv` values per thread and channel (acc[k][c], k < nv valid ones), written to
+// part[PART_STRIDE].  Two-pass inside each warp (mean first, then centred squares) and Chan's merge across warps:
+// no E[x^2] - mean^2 cancellation anywhere.
+template <int NT, int NV>
+__device__ __forceinline__ void block_stats(const float (&acc)[NV][C1], int nvalid, float* __restrict__ part,
+                                            float (*red)[PART_STRIDE]) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nw = warp_sum_i(nvalid);
+#pragma unroll
+    for (int c = 0; c < C1; ++c) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) if (k < nvalid) s += acc[k][c];
+        s = warp_sum(s);
+        const float mean = nw > 0 ? s / (float)nw : 0.f;
+        float m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) if (k < nvalid) { float dlt = acc[k][c] - mean; m2 = fmaf(dlt, dlt, m2); }
+        m2 = warp_sum(m2);
+        if (lane == 0) { red[wid][c] = mean; red[wid][C1 + c] = m2; }
+    }
+    if (lane == 0) red[wid][2 * C1] = (float)nw;
+    __syncthreads();
+    if (tid < C1) {
+        float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) {
+            float cnt = red[w][2 * C1];
+            if (cnt > 0.f) {
+                float delta = red[w][tid] - mean, nt = n + cnt;
+                mean += delta * cnt / nt;
+                M2 += red[w][C1 + tid] + delta * delta * n * cnt / nt;
+                n = nt;
+            }
+        }
+        part[tid] = mean; part[C1 + tid] = M2;
+        if (tid == 0) part[2 * C1] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ posenc
+// positional_encoding (hybrid_encoder.py:56-67): per pose p[6] -> [sin(p_i * f), ...] then [cos(...)], f in {1,2},
+// order (i major, f minor); 24 values per pose.
+__global__ void posenc_kernel(const float* __restrict__ obs, int64_t obs_stride, float* __restrict__ pe, int B, int S) {
+    // S = buffer_size * 6 state values per row; output [B, 4*S]
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)B * S) return;
+    int b = (int)(idx / S), s = (int)(idx - (int64_t)b * S);
+    int pose = s / 6, i = s - pose * 6;
+    float x = obs[(int64_t)b * obs_stride + s];
+    float* o = pe + (int64_t)b * 4 * S + pose * 24;
+    float x1 = x * 1.0f, x2 = x * 2.0f;
+    o[2 * i] = sinf(x1); o[2 * i + 1] = sinf(x2);
+    o[12 + 2 * i] = cosf(x1); o[12 + 2 * i + 1] = cosf(x2);
+}
+
+// ------------------------------------------------------------------------------------------------ conv1
+// Conv3d(1,16,3,stride 2) on the grid columns of the observation.  y1 [B, G1^3, 16] (pre-BN, channels-last).
+// Per-block partial (sum, sumsq) per channel -> part[blk][32] when stats != nullptr.
+__global__ void __launch_bounds__(CONV1_THREADS)
+conv1_fwd_kernel(const float* __restrict__ obs, int64_t obs_stride, int64_t grid_off, const float* __restrict__ w,
+                 const float* __restrict__ bias, float* __restrict__ y1, float* __restrict__ part, int G, int G1) {
+    __shared__ __align__(16) float ws[TAPS][C1];
+    __shared__ float bs[C1];
+    __shared__ float red[CONV1_THREADS / 32][PART_STRIDE];
+    const int tid = threadIdx.x, b = blockIdx.y;
+    for (int i = tid; i < TAPS * C1; i += CONV1_THREADS) {
+        int tap = i / C1, c = i - tap * C1;
+        ws[tap][c] = w[c * TAPS + tap];                 // weight [16,1,3,3,3]
+    }
+    if (tid < C1) bs[tid] = bias[tid];
+    __syncthreads();
+    const int P1 = G1 * G1 * G1;
+    const int p = blockIdx.x * CONV1_THREADS + tid;
+    float acc1[1][C1];
+    float (&acc)[C1] = acc1[0];
+    const bool valid = p < P1;
+    if (valid) {
+        int z1 = p % G1, t = p / G1;
+        int yy = t % G1, xx = t / G1;
+        const float* in = obs + (int64_t)b * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
+#pragma unroll
+        for (int c = 0; c < C1; ++c) acc[c] = bs[c];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    float v = __ldg(in + ((int64_t)i * G + j) * G + l);
+                    const float4* wr = reinterpret_cast<const float4*>(ws[(i * 3 + j) * 3 + l]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 wv = wr[q];
+                        acc[4 * q + 0] = fmaf(v, wv.x, acc[4 * q + 0]);
+                        acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+                        acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+                        acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+                    }
+                }
+        float4* o = reinterpret_cast<float4*>(y1 + ((int64_t)b * P1 + p) * C1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C1; ++c) acc[c] = 0.f;
+    }
+    if (part)
+        block_stats<CONV1_THREADS, 1>(acc1, valid ? 1 : 0, part + ((int64_t)b * gridDim.x + blockIdx.x) * PART_STRIDE, red);
+}
+
+// ------------------------------------------------------------------------------------------------ BN statistics
+// Merges the per-block (count, mean, M2) partials (Chan et al.) in double in a fixed order -- 32 lanes per channel
+// stride over the blocks, then a 5-step butterfly -- and produces the affine form y = a*x + b.  In training mode it
+// also updates the running statistics like nn.BatchNorm3d (biased variance to normalise, unbiased for running_var,
+// momentum 0.1, eps 1e-5).  stat layout [4][16]: mean, invstd, a, b.
+__device__ __forceinline__ void chan_merge(double& n, double& mean, double& M2, double nb, double mb, double M2b) {
+    if (nb <= 0) return;
+    double nt = n + nb, delta = mb - mean;
+    mean += delta * nb / nt;
+    M2 += M2b + delta * delta * n * nb / nt;
+    n = nt;
+}
+
+__global__ void __launch_bounds__(32 * C1)
+bn_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                   int64_t* __restrict__ num_batches_tracked, float* __restrict__ stat, float eps, float momentum) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double n = 0, mean = 0, M2 = 0;
+    for (int k = lane; k < nblk; k += 32) {
+        const float* pr = part + (int64_t)k * PART_STRIDE;
+        chan_merge(n, mean, M2, (double)pr[2 * C1], (double)pr[c], (double)pr[C1 + c]);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+               M2b = __shfl_xor_sync(0xffffffffu, M2, o);
+        // merge in a lane-symmetric way so that both partners obtain identical results
+        double n_lo = (lane & o) ? nb : n, m_lo = (lane & o) ? mb : mean, q_lo = (lane & o) ? M2b : M2;
+        double n_hi = (lane & o) ? n : nb, m_hi = (lane & o) ? mean : mb, q_hi = (lane & o) ? M2 : M2b;
+        chan_merge(n_lo, m_lo, q_lo, n_hi, m_hi, q_hi);
+        n = n_lo; mean = m_lo; M2 = q_lo;
+    }
+    if (lane != 0) return;
+    double var = n > 0 ? M2 / n : 0.0;
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float a = gamma[c] * invstd;
+    stat[0 * C1 + c] = (float)mean;
+    stat[1 * C1 + c] = invstd;
+    stat[2 * C1 + c] = a;
+    stat[3 * C1 + c] = beta[c] - (float)mean * a;
+    if (running_mean) {
+        double unbiased = n > 1 ? M2 / (n - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+        if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    }
+}
+
+// eval mode: a = gamma / sqrt(running_var + eps), b = beta - running_mean * a
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float* __restrict__ stat, float eps) {
+    const int c = threadIdx.x;
+    if (c >= C1) return;
+    float invstd = 1.0f / sqrtf(running_var[c] + eps);
+    float a = gamma[c] * invstd;
+    stat[0 * C1 + c] = running_mean[c];
+    stat[1 * C1 + c] = invstd;
+    stat[2 * C1 + c] = a;
+    stat[3 * C1 + c] = beta[c] - running_mean[c] * a;
+}
+
+// ------------------------------------------------------------------------------------------------ conv2
+// Conv3d(16,16,3,stride 2) as an implicit GEMM; input y1 [B,G1^3,16] with BN1 affine + ReLU applied on load,
+// output y2 [B,16,G2^3] (pre-BN, channel-major = the order nn.Flatten feeds the grid Linear).
+__global__ void __launch_bounds__(CONV2_THREADS)
+conv2_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ w,
+                 const float* __restrict__ bias, float* __restrict__ y2, float* __restrict__ part, int G1, int G2) {
+    __shared__ __align__(16) float ws[TAPS][C1][C1];        // [tap][ci][co]
+    __shared__ float a1s[C1], b1s[C1], bs[C1];
+    __shared__ float red[CONV2_THREADS / 32][PART_STRIDE];
+    const int tid = threadIdx.x, b = blockIdx.y;
+    for (int i = tid; i < TAPS * C1 * C1; i += CONV2_THREADS) {
+        int tap = i / (C1 * C1), r = i - tap * C1 * C1, ci = r / C1, co = r - ci * C1;
+        ws[tap][ci][co] = w[(co * C1 + ci) * TAPS + tap];    // weight [16,16,3,3,3]
+    }
+    if (tid < C1) { a1s[tid] = stat1[2 * C1 + tid]; b1s[tid] = stat1[3 * C1 + tid]; bs[tid] = bias[tid]; }
+    __syncthreads();
+    const int ZQ = (G2 + CONV2_ZT - 1) / CONV2_ZT;
+    const int items = G2 * G2 * ZQ;
+    const int item = blockIdx.x * CONV2_THREADS + tid;
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    float acc[CONV2_ZT][C1];
+    const bool active = item < items;
+    int x2 = 0, yy2 = 0, z20 = 0;
+    if (active) {
+        int q = item % ZQ, t = item / ZQ;
+        yy2 = t % G2; x2 = t / G2; z20 = q * CONV2_ZT;
+#pragma unroll
+        for (int s = 0; s < CONV2_ZT; ++s)
+#pragma unroll
+            for (int c = 0; c < C1; ++c) acc[s][c] = bs[c];
+        const float* in_b = y1 + (int64_t)b * P1 * C1;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                const float* row = in_b + (((int64_t)(2 * x2 + i) * G1 + (2 * yy2 + j)) * G1) * C1;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const int tap = (i * 3 + j) * 3 + l;
+#pragma unroll
+                    for (int cq = 0; cq < 4; ++cq) {             // 4 input channels at a time
+                        float4 xin[CONV2_ZT];
+                        const float4 av = *reinterpret_cast<const float4*>(&a1s[4 * cq]);
+                        const float4 bv = *reinterpret_cast<const float4*>(&b1s[4 * cq]);
+#pragma unroll
+                        for (int s = 0; s < CONV2_ZT; ++s) {
+                            int zi = 2 * (z20 + s) + l;
+                            zi = min(zi, G1 - 1);               // out-of-range lanes (z2 >= G2) read a valid voxel, result unused
+                            float4 v = __ldg(reinterpret_cast<const float4*>(row + (int64_t)zi * C1) + cq);
+                            v.x = fmaxf(fmaf(av.x, v.x, bv.x), 0.f); v.y = fmaxf(fmaf(av.y, v.y, bv.y), 0.f);
+                            v.z = fmaxf(fmaf(av.z, v.z, bv.z), 0.f); v.w = fmaxf(fmaf(av.w, v.w, bv.w), 0.f);
+                            xin[s] = v;
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 4; ++cc) {
+                            const float4* wr = reinterpret_cast<const float4*>(ws[tap][4 * cq + cc]);
+#pragma unroll
+                            for (int oq = 0; oq < 4; ++oq) {
+                                const float4 wv = wr[oq];
+#pragma unroll
+                                for (int s = 0; s < CONV2_ZT; ++s) {
+                                    const float xv = cc == 0 ? xin[s].x : (cc == 1 ? xin[s].y : (cc == 2 ? xin[s].z : xin[s].w));
+                                    acc[s][4 * oq + 0] = fmaf(xv, wv.x, acc[s][4 * oq + 0]);
+                                    acc[s][4 * oq + 1] = fmaf(xv, wv.y, acc[s][4 * oq + 1]);
+                                    acc[s][4 * oq + 2] = fmaf(xv, wv.z, acc[s][4 * oq + 2]);
+                                    acc[s][4 * oq + 3] = fmaf(xv, wv.w, acc[s][4 * oq + 3]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        const int pbase = (x2 * G2 + yy2) * G2;
+#pragma unroll
+        for (int s = 0; s < CONV2_ZT; ++s) {
+            int z2 = z20 + s;
+            if (z2 < G2) {
+#pragma unroll
+                for (int c = 0; c < C1; ++c) y2[((int64_t)b * C1 + c) * P2 + pbase + z2] = acc[s][c];
+            }
+        }
+    }
+    if (part) {
+        const int nvalid = active ? min(CONV2_ZT, G2 - z20) : 0;
+        block_stats<CONV2_THREADS, CONV2_ZT>(acc, nvalid, part + ((int64_t)b * gridDim.x + blockIdx.x) * PART_STRIDE, red);
+    }
+}
+
+// act2 = relu(a2[c] * y2 + b2[c]), [B,16,P2] channel-major
+__global__ void bn_relu_apply_kernel(const float* __restrict__ y2, const float* __restrict__ stat2, float* __restrict__ act2,
+                                     int64_t total, int P2) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    int c = (int)((idx / P2) % C1);
+    act2[idx] = fmaxf(fmaf(stat2[2 * C1 + c], y2[idx], stat2[3 * C1 + c]), 0.f);
+}
+
+
+// =====================================================================================================================
+// backward kernels
+// =====================================================================================================================
+
+// dy[i,j] = y[i,j] > 0 ? dy[i,j] : 0   (ReLU backward from the stored post-activation), row-strided buffers
+__global__ void relu_mask_kernel(const float* __restrict__ dy_in, int64_t ldi, float* __restrict__ dy, int64_t ldd,
+                                 const float* __restrict__ y, int64_t ldy, int rows, int cols) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)rows * cols) return;
+    int r = (int)(idx / cols), c = (int)(idx - (int64_t)r * cols);
+    dy[(int64_t)r * ldd + c] = (y[(int64_t)r * ldy + c] > 0.f) ? dy_in[(int64_t)r * ldi + c] : 0.f;
+}
+
+// db[j] = sum_i dy[i,j]  (rows summed in order: deterministic)
+__global__ void colsum_kernel(const float* __restrict__ dy, int64_t ld, int rows, int cols, float* __restrict__ db) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    float s = 0.f;
+    for (int i = 0; i < rows; ++i) s += dy[(int64_t)i * ld + j];
+    db[j] = s;
+}
+
+// BN2 backward, pass 1: per (sample, channel) sums of g = dact2 * [act2 > 0] and g * xhat.  part [B][16][2]
+__global__ void __launch_bounds__(256)
+bn2_bwd_reduce_kernel(const float* __restrict__ dact2, const float* __restrict__ act2, const float* __restrict__ y2,
+                      const float* __restrict__ stat2, float* __restrict__ part, int P2) {
+    __shared__ float sh[2][8];
+    const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int64_t base = ((int64_t)b * C1 + c) * P2;
+    const float mean = stat2[c], invstd = stat2[C1 + c];
+    float s1 = 0.f, s2 = 0.f;
+    for (int p = tid; p < P2; p += 256) {
+        float g = act2[base + p] > 0.f ? dact2[base + p] : 0.f;
+        s1 += g;
+        s2 = fmaf(g, (y2[base + p] - mean) * invstd, s2);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((tid & 31) == 0) { sh[0][tid >> 5] = s1; sh[1][tid >> 5] = s2; }
+    __syncthreads();
+    if (tid < 2) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += sh[tid][w];
+        part[((int64_t)b * C1 + c) * 2 + tid] = t;
+    }
+}
+
+// Sums `nrec` records of (S1[16], S2[16]) laid out as rec[k][c*2 + {0,1}] (layout A) or rec[k][{0,1}*16 + c] (layout B)
+// in double, fixed order; writes d_gamma = S2, d_beta = S1 and coef[2][16] = S1/n, S2/n.
+__global__ void __launch_bounds__(32 * C1)
+bn_bwd_finalize_kernel(const float* __restrict__ rec, int nrec, int rec_stride, int layout_b, double count,
+                       float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef, int zero_coef) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double s1 = 0, s2 = 0;
+    for (int k = lane; k < nrec; k += 32) {
+        const float* r = rec + (int64_t)k * rec_stride;
+        s1 += layout_b ? r[c] : r[c * 2];
+        s2 += layout_b ? r[C1 + c] : r[c * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) {
+        dgamma[c] = (float)s2; dbeta[c] = (float)s1;
+        // eval-mode BN is a fixed affine map: no batch-statistics terms in dx
+        coef[c] = zero_coef ? 0.f : (float)(s1 / count); coef[C1 + c] = zero_coef ? 0.f : (float)(s2 / count);
+    }
+}
+
+// BN2 backward, pass 2: dy2 = a2 * (g - S1/n - xhat * S2/n), written channels-last [B,P2,16] for the conv2 backward kernels
+__global__ void __launch_bounds__(256)
+bn2_bwd_apply_kernel(const float* __restrict__ dact2, const float* __restrict__ act2, const float* __restrict__ y2,
+                     const float* __restrict__ stat2, const float* __restrict__ coef, float* __restrict__ dy2cl, int P2) {
+    const int b = blockIdx.y, p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= P2) return;
+    float out[C1];
+#pragma unroll
+    for (int c = 0; c < C1; ++c) {
+        const int64_t i = ((int64_t)b * C1 + c) * P2 + p;
+        const float g = act2[i] > 0.f ? dact2[i] : 0.f;
+        const float xhat = (y2[i] - stat2[c]) * stat2[C1 + c];
+        out[c] = stat2[2 * C1 + c] * (g - coef[c] - xhat * coef[C1 + c]);
+    }
+    float4* o = reinterpret_cast<float4*>(dy2cl + ((int64_t)b * P2 + p) * C1);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+}
+
+// conv2 weight gradient.  Block = 4 position streams x 64 threads; thread (ci, cg) owns dW2[co = 4cg..4cg+3][ci][27 taps]
+// (108 accumulators).  dW2[co,ci,tap] = sum_{b,pos} dy2[b,pos,co] * relu(bn1(y1))[b, 2pos+tap, ci].
+// Partials: part[blk][6912 + 16] in weight layout [co][ci][tap] followed by db2[16].
+constexpr int WG2_THREADS = 256;
+constexpr int WG2_POS_PER_STREAM = 32;
+constexpr int WG2_REC = C1 * C1 * TAPS + C1;
+__global__ void __launch_bounds__(WG2_THREADS)
+conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
+                   float* __restrict__ part, int G1, int G2, int64_t total_pos) {
+    extern __shared__ float sred[];           // [3][WG2_REC] for the cross-stream reduction
+    const int tid = threadIdx.x, stream = tid >> 6, t64 = tid & 63, ci = t64 >> 2, cg = t64 & 3;
+    const float a1 = stat1[2 * C1 + ci], b1 = stat1[3 * C1 + ci];
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    float acc[TAPS][4];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t pos0 = ((int64_t)blockIdx.x * 4 + stream) * WG2_POS_PER_STREAM;
+    for (int k = 0; k < WG2_POS_PER_STREAM; ++k) {
+        const int64_t gp = pos0 + k;
+        if (gp >= total_pos) break;
+        const int b = (int)(gp / P2), p = (int)(gp - (int64_t)b * P2);
+        const int z2 = p % G2, t = p / G2, yy2 = t % G2, x2 = t / G2;
+        const float4 dy = __ldg(reinterpret_cast<const float4*>(dy2cl + gp * C1) + cg);
+        if (ci == 0) { dbs.x += dy.x; dbs.y += dy.y; dbs.z += dy.z; dbs.w += dy.w; }
+        const float* in = y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2) * G1 + 2 * yy2) * G1 + 2 * z2) * C1 + ci;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    float x = __ldg(in + (((int64_t)i * G1 + j) * G1 + l) * C1);
+                    x = fmaxf(fmaf(a1, x, b1), 0.f);
+                    const int tap = (i * 3 + j) * 3 + l;
+                    acc[tap][0] = fmaf(dy.x, x, acc[tap][0]); acc[tap][1] = fmaf(dy.y, x, acc[tap][1]);
+                    acc[tap][2] = fmaf(dy.z, x, acc[tap][2]); acc[tap][3] = fmaf(dy.w, x, acc[tap][3]);
+                }
+    }
+    // cross-stream reduction in a fixed order: streams 1..3 publish, stream 0 adds them in order and writes the record
+    if (stream > 0) {
+        float* dst = sred + (stream - 1) * WG2_REC;
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[((4 * cg + q) * C1 + ci) * TAPS + t] = acc[t][q];
+        if (ci == 0) { dst[C1 * C1 * TAPS + 4 * cg + 0] = dbs.x; dst[C1 * C1 * TAPS + 4 * cg + 1] = dbs.y;
+                       dst[C1 * C1 * TAPS + 4 * cg + 2] = dbs.z; dst[C1 * C1 * TAPS + 4 * cg + 3] = dbs.w; }
+    }
+    __syncthreads();
+    if (stream == 0) {
+        float* out = part + (int64_t)blockIdx.x * WG2_REC;
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int o = ((4 * cg + q) * C1 + ci) * TAPS + t;
+                out[o] = ((acc[t][q] + sred[o]) + sred[WG2_REC + o]) + sred[2 * WG2_REC + o];
+            }
+        if (ci == 0) {
+            const float d4[4] = {dbs.x, dbs.y, dbs.z, dbs.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int o = C1 * C1 * TAPS + 4 * cg + q;
+                out[o] = ((d4[q] + sred[o]) + sred[WG2_REC + o]) + sred[2 * WG2_REC + o];
+            }
+        }
+    }
+}
+
+// out[j] = sum_k part[k][j] for j < rec (fixed order, double accumulation); out split over two destinations
+__global__ void __launch_bounds__(256)
+reduce_records_kernel(const float* __restrict__ part, int nrec, int rec, float* __restrict__ out_a, int na,
+                      float* __restrict__ out_b) {
+    const int j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= rec) return;
+    double s = 0.0;
+    for (int k = 0; k < nrec; ++k) s += (double)part[(int64_t)k * rec + j];
+    if (j < na) out_a[j] = (float)s;
+    else out_b[j - na] = (float)s;
+}
+
+// conv2 data gradient + ReLU/BN1 backward statistics.  One thread per conv1-output voxel, 16 input channels.
+//   dact1[b,vi,ci] = sum_{taps with (vi - tap) even and in range} sum_co dy2[b,(vi-tap)/2,co] * W2[co,ci,tap]
+//   g1 = dact1 * [bn1(y1) > 0]  -> stored channels-last; per-block (sum g1, sum g1*xhat1) partials -> bpart[blk][32]
+constexpr int DG2_THREADS = 128;
+__global__ void __launch_bounds__(DG2_THREADS)
+conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w, const float* __restrict__ y1,
+                   const float* __restrict__ stat1, float* __restrict__ g1, float* __restrict__ bpart, int G1, int G2) {
+    __shared__ __align__(16) float ws[TAPS][C1][C1];        // [tap][co][ci]
+    __shared__ float red[DG2_THREADS / 32][2 * C1];
+    const int tid = threadIdx.x, b = blockIdx.y;
+    for (int i = tid; i < TAPS * C1 * C1; i += DG2_THREADS) {
+        int tap = i / (C1 * C1), r = i - tap * C1 * C1, co = r / C1, ci = r - co * C1;
+        ws[tap][co][ci] = w[(co * C1 + ci) * TAPS + tap];
+    }
+    __syncthreads();
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    const int p = blockIdx.x * DG2_THREADS + tid;
+    const bool valid = p < P1;
+    float acc[C1];
+#pragma unroll
+    for (int c = 0; c < C1; ++c) acc[c] = 0.f;
+    float s1[C1], s2[C1];
+    if (valid) {
+        const int zi = p % G1, t = p / G1, yi = t % G1, xi = t / G1;
+        for (int i = 0; i < 3; ++i) {
+            const int xr = xi - i;
+            if (xr < 0 || (xr & 1) || (xr >> 1) >= G2) continue;
+            for (int j = 0; j < 3; ++j) {
+                const int yr = yi - j;
+                if (yr < 0 || (yr & 1) || (yr >> 1) >= G2) continue;
+                for (int l = 0; l < 3; ++l) {
+                    const int zr = zi - l;
+                    if (zr < 0 || (zr & 1) || (zr >> 1) >= G2) continue;
+                    const int tap = (i * 3 + j) * 3 + l;
+                    const int64_t p2 = ((int64_t)(xr >> 1) * G2 + (yr >> 1)) * G2 + (zr >> 1);
+                    const float4* dyp = reinterpret_cast<const float4*>(dy2cl + ((int64_t)b * P2 + p2) * C1);
+#pragma unroll
+                    for (int oq = 0; oq < 4; ++oq) {
+                        const float4 dv = __ldg(dyp + oq);
+                        const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+                        for (int oo = 0; oo < 4; ++oo) {
+                            const float4* wr = reinterpret_cast<const float4*>(ws[tap][4 * oq + oo]);
+#pragma unroll
+                            for (int cq = 0; cq < 4; ++cq) {
+                                const float4 wv = wr[cq];
+                                acc[4 * cq + 0] = fmaf(d4[oo], wv.x, acc[4 * cq + 0]);
+                                acc[4 * cq + 1] = fmaf(d4[oo], wv.y, acc[4 * cq + 1]);
+                                acc[4 * cq + 2] = fmaf(d4[oo], wv.z, acc[4 * cq + 2]);
+                                acc[4 * cq + 3] = fmaf(d4[oo], wv.w, acc[4 * cq + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const float4* yp = reinterpret_cast<const float4*>(y1 + ((int64_t)b * P1 + p) * C1);
+        float4* gp = reinterpret_cast<float4*>(g1 + ((int64_t)b * P1 + p) * C1);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 yv = __ldg(yp + q);
+            const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+            float o4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int c = 4 * q + e;
+                const float pre = fmaf(stat1[2 * C1 + c], y4[e], stat1[3 * C1 + c]);
+                const float g = pre > 0.f ? acc[c] : 0.f;
+                o4[e] = g;
+                s1[c] = g;
+                s2[c] = g * ((y4[e] - stat1[c]) * stat1[C1 + c]);
+            }
+            gp[q] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < C1; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+    }
+#pragma unroll
+    for (int c = 0; c < C1; ++c) {
+        float a = warp_sum(s1[c]), q = warp_sum(s2[c]);
+        if ((tid & 31) == 0) { red[tid >> 5][c] = a; red[tid >> 5][C1 + c] = q; }
+    }
+    __syncthreads();
+    if (tid < 2 * C1) {
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < DG2_THREADS / 32; ++wv) t += red[wv][tid];
+        bpart[((int64_t)b * gridDim.x + blockIdx.x) * 2 * C1 + tid] = t;
+    }
+}
+
+// conv1 weight gradient with the BN1 backward applied on the fly:
+//   dy1 = a1 * (g1 - S1/n - xhat1 * S2/n);  dW1[co,tap] = sum dy1[b,p,co] * tri[b, 2p+tap];  db1[co] = sum dy1
+// Groups of 8 threads share a position: thread (cg, th) owns co = 4cg..4cg+3 and taps [14*th, min(27, 14*th+14)).
+constexpr int WG1_THREADS = 256;
+constexpr int WG1_POS_PER_STREAM = 64;
+constexpr int WG1_REC = C1 * TAPS + C1;
+__global__ void __launch_bounds__(WG1_THREADS)
+conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, int64_t grid_off, const float* __restrict__ g1,
+                   const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ coef,
+                   float* __restrict__ part, int G, int G1, int64_t total_pos) {
+    __shared__ float red[WG1_THREADS / 32][WG1_REC];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int grp = tid >> 3, t8 = tid & 7, cg = t8 >> 1, th = t8 & 1;
+    const int P1 = G1 * G1 * G1;
+    float acc[14][4];
+#pragma unroll
+    for (int t = 0; t < 14; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    float dbs[4] = {0.f, 0.f, 0.f, 0.f};
+    float a1[4], mean[4], invstd[4], k1[4], k2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = 4 * cg + q;
+        mean[q] = stat1[c]; invstd[q] = stat1[C1 + c]; a1[q] = stat1[2 * C1 + c]; k1[q] = coef[c]; k2[q] = coef[C1 + c];
+    }
+    const int64_t pos0 = ((int64_t)blockIdx.x * (WG1_THREADS / 8) + grp) * WG1_POS_PER_STREAM;
+    for (int k = 0; k < WG1_POS_PER_STREAM; ++k) {
+        const int64_t gp = pos0 + k;
+        if (gp >= total_pos) break;
+        const int b = (int)(gp / P1), p = (int)(gp - (int64_t)b * P1);
+        const int z1 = p % G1, t = p / G1, yy = t % G1, xx = t / G1;
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g1 + gp * C1) + cg);
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(y1 + gp * C1) + cg);
+        const float g4[4] = {gv.x, gv.y, gv.z, gv.w}, y4[4] = {yv.x, yv.y, yv.z, yv.w};
+        float dy[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dy[q] = a1[q] * (g4[q] - k1[q] - ((y4[q] - mean[q]) * invstd[q]) * k2[q]);
+            if (th == 0) dbs[q] += dy[q];
+        }
+        const float* in = obs + (int64_t)b * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
+#pragma unroll
+        for (int tt = 0; tt < 14; ++tt) {
+            const int tap = 14 * th + tt;
+            if (tap < TAPS) {
+                const int i = tap / 9, j = (tap / 3) % 3, l = tap % 3;
+                const float v = __ldg(in + ((int64_t)i * G + j) * G + l);
+                acc[tt][0] = fmaf(dy[0], v, acc[tt][0]); acc[tt][1] = fmaf(dy[1], v, acc[tt][1]);
+                acc[tt][2] = fmaf(dy[2], v, acc[tt][2]); acc[tt][3] = fmaf(dy[3], v, acc[tt][3]);
+            }
+        }
+    }
+    // reduce the 4 groups of a warp (lanes differing in bits 3,4), then the 8 warps in order
+#pragma unroll
+    for (int tt = 0; tt < 14; ++tt)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v = acc[tt][q];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[tt][q] = v;
+        }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v = dbs[q];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        dbs[q] = v;
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int tt = 0; tt < 14; ++tt) {
+            const int tap = 14 * th + tt;
+            if (tap < TAPS) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) red[wid][(4 * cg + q) * TAPS + tap] = acc[tt][q];
+            }
+        }
+        if (th == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[wid][C1 * TAPS + 4 * cg + q] = dbs[q];
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < WG1_REC; j += WG1_THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < WG1_THREADS / 32; ++w) t += red[w][j];
+        part[(int64_t)blockIdx.x * WG1_REC + j] = t;
+    }
+}
+
+}  // namespace gnbv
+
+using namespace gnbv;
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+namespace {
+
+struct EncDims {
+    int B, G, G1, G2, P1, P2, S, FEAT, HID;
+    int nblk1, nblk2, items2;
+    int64_t flat2;
+};
+
+EncDims make_dims(int B, int G, int state_dim) {
+    EncDims d;
+    d.B = B; d.G = G;
+    d.G1 = (G - 3) / 2 + 1;
+    d.G2 = (d.G1 - 3) / 2 + 1;
+    d.P1 = d.G1 * d.G1 * d.G1; d.P2 = d.G2 * d.G2 * d.G2;
+    d.S = state_dim; d.FEAT = 256; d.HID = 256;
+    d.nblk1 = (int)ceil_div(d.P1, CONV1_THREADS);
+    d.items2 = d.G2 * d.G2 * (int)ceil_div(d.G2, CONV2_ZT);
+    d.nblk2 = (int)ceil_div(d.items2, CONV2_THREADS);
+    d.flat2 = (int64_t)C1 * d.P2;
+    return d;
+}
+
+// workspace carve-up (floats). Forward activations that backward needs stay here between the two calls.
+struct EncWs {
+    size_t pe, h1, cat, y1, part1, stat1, y2, part2, stat2, act2, gemm, total;
+    // backward-only
+    size_t dz, dcat, dh1, dact2, dy2cl, g1, bn2part, coef2, bpart1, coef1, wg2part, wg1part;
+    int nblk_dg, nblk_wg2, nblk_wg1;
+};
+
+EncWs make_ws(const EncDims& d, bool backward) {
+    EncWs w;
+    size_t o = 0;
+    auto take = [&](size_t n) { size_t r = o; o += (n + 63) & ~(size_t)63; return r; };
+    const size_t B = d.B;
+    w.pe = take(B * 4 * d.S);
+    w.h1 = take(B * d.HID);
+    w.cat = take(B * 2 * d.HID);
+    w.y1 = take(B * (size_t)d.P1 * C1);
+    w.part1 = take(B * (size_t)d.nblk1 * PART_STRIDE);
+    w.stat1 = take(4 * C1);
+    w.y2 = take(B * (size_t)d.flat2);
+    w.part2 = take(B * (size_t)d.nblk2 * PART_STRIDE);
+    w.stat2 = take(4 * C1);
+    w.act2 = take(B * (size_t)d.flat2);
+    size_t g = 0;
+    g = std::max(g, gemm_workspace_floats(d.B, d.HID, 4 * d.S));
+    g = std::max(g, gemm_workspace_floats(d.B, d.HID, d.HID));
+    g = std::max(g, gemm_workspace_floats(d.B, d.HID, (int)d.flat2));
+    g = std::max(g, gemm_workspace_floats(d.B, d.FEAT, 2 * d.HID));
+    w.dz = w.dcat = w.dh1 = w.dact2 = w.dy2cl = w.g1 = w.bn2part = w.coef2 = w.bpart1 = w.coef1 = w.wg2part = w.wg1part = 0;
+    w.nblk_dg = (int)ceil_div(d.P1, DG2_THREADS);
+    w.nblk_wg2 = (int)ceil_div((int64_t)d.B * d.P2, 4 * WG2_POS_PER_STREAM);
+    w.nblk_wg1 = (int)ceil_div((int64_t)d.B * d.P1, (WG1_THREADS / 8) * WG1_POS_PER_STREAM);
+    if (backward) {
+        w.dz = take(B * d.FEAT);
+        w.dcat = take(B * 2 * d.HID);
+        w.dh1 = take(B * d.HID);
+        w.dact2 = take(B * (size_t)d.flat2);
+        w.dy2cl = take(B * (size_t)d.flat2);
+        w.g1 = take(B * (size_t)d.P1 * C1);
+        w.bn2part = take(B * C1 * 2);
+        w.coef2 = take(2 * C1);
+        w.bpart1 = take(B * (size_t)w.nblk_dg * 2 * C1);
+        w.coef1 = take(2 * C1);
+        w.wg2part = take((size_t)w.nblk_wg2 * WG2_REC);
+        w.wg1part = take((size_t)w.nblk_wg1 * WG1_REC);
+        g = std::max(g, gemm_workspace_floats(d.B, 2 * d.HID, d.FEAT));
+        g = std::max(g, gemm_workspace_floats(d.FEAT, 2 * d.HID, d.B));
+        g = std::max(g, gemm_workspace_floats(d.B, (int)d.flat2, d.HID));
+        g = std::max(g, gemm_workspace_floats(d.HID, (int)d.flat2, d.B));
+        g = std::max(g, gemm_workspace_floats(d.HID, 4 * d.S, d.B));
+        g = std::max(g, gemm_workspace_floats(d.HID, d.HID, d.B));
+        g = std::max(g, gemm_workspace_floats(d.B, d.HID, d.HID));
+    }
+    w.gemm = take(g);
+    w.total = o;
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t gnbv_encoder_workspace_bytes(int batch, int grid_size, int state_dim, int with_backward) {
+    if (batch <= 0 || grid_size < 7 || state_dim <= 0) return 0;
+    EncDims d = make_dims(batch, grid_size, state_dim);
+    return make_ws(d, with_backward != 0).total * 4 + 256;
+}
+
+extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride, int batch,
+                                    int grid_size, int state_dim, int training, float* features, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GNBV_REQUIRE(p && obs && features && workspace, "gnbv_encoder_forward: null pointer argument");
+    GNBV_REQUIRE(batch > 0 && grid_size >= 7 && state_dim > 0 && state_dim % 6 == 0,
+                 "gnbv_encoder_forward: bad sizes (batch=%d grid=%d state=%d)", batch, grid_size, state_dim);
+    GNBV_REQUIRE(p->conv1_w && p->conv1_b && p->bn1_w && p->bn1_b && p->bn1_rm && p->bn1_rv && p->conv2_w && p->conv2_b &&
+                     p->bn2_w && p->bn2_b && p->bn2_rm && p->bn2_rv && p->grid_fc_w && p->grid_fc_b && p->act_fc1_w &&
+                     p->act_fc1_b && p->act_fc2_w && p->act_fc2_b && p->out_fc_w && p->out_fc_b,
+                 "gnbv_encoder_forward: null parameter pointer");
+    EncDims d = make_dims(batch, grid_size, state_dim);
+    GNBV_REQUIRE(d.G2 >= 1, "gnbv_encoder_forward: grid too small");
+    // the forward-only and forward+backward layouts share every forward offset (backward buffers are appended
+    // before the GEMM scratch, which is re-derived per call), so the forward layout is the prefix of both
+    EncWs w = make_ws(d, false);
+    GNBV_REQUIRE(workspace_bytes >= w.total * 4, "gnbv_encoder_forward: workspace %zu B < %zu B", workspace_bytes, w.total * 4);
+    if (workspace_bytes >= make_ws(d, true).total * 4) w = make_ws(d, true);
+    GNBV_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)obs & 15) == 0 && obs_row_stride % 4 == 0 && state_dim % 4 == 0,
+                 "gnbv_encoder_forward: workspace must be 256 B aligned, obs rows 16 B aligned");
+    float* ws = reinterpret_cast<float*>(workspace);
+    const int B = batch;
+    GemmEpilogue relu_ep;
+    relu_ep.relu = 1;
+    int rc;
+    // ---- action branch: positional encoding -> Linear(4S,256)+ReLU -> Linear(256,256)+ReLU (written into cat[:, :256])
+    posenc_kernel<<<(unsigned)ceil_div((int64_t)B * d.S, 256), 256, 0, stream>>>(obs, obs_row_stride, ws + w.pe, B, d.S);
+    GNBV_LAUNCH_CHECK("posenc_kernel");
+    relu_ep.bias = p->act_fc1_b;
+    rc = launch_gemm(ws + w.pe, 4 * d.S, 1, p->act_fc1_w, 1, 4 * d.S, ws + w.h1, d.HID, B, d.HID, 4 * d.S, relu_ep, ws + w.gemm, stream);
+    if (rc) return rc;
+    relu_ep.bias = p->act_fc2_b;
+    rc = launch_gemm(ws + w.h1, d.HID, 1, p->act_fc2_w, 1, d.HID, ws + w.cat, 2 * d.HID, B, d.HID, d.HID, relu_ep, ws + w.gemm, stream);
+    if (rc) return rc;
+    // ---- grid branch
+    float* part1 = training ? ws + w.part1 : nullptr;
+    conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, state_dim, p->conv1_w, p->conv1_b,
+                                                                      ws + w.y1, part1, d.G, d.G1);
+    GNBV_LAUNCH_CHECK("conv1_fwd_kernel");
+    if (training)
+        bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(part1, B * d.nblk1, p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, p->bn1_nbt,
+                                                      ws + w.stat1, 1e-5f, 0.1f);
+    else
+        bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, ws + w.stat1, 1e-5f);
+    GNBV_LAUNCH_CHECK("bn1 statistics");
+    float* part2 = training ? ws + w.part2 : nullptr;
+    conv2_fwd_kernel<<<dim3(d.nblk2, B), CONV2_THREADS, 0, stream>>>(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2,
+                                                                      part2, d.G1, d.G2);
+    GNBV_LAUNCH_CHECK("conv2_fwd_kernel");
+    if (training)
+        bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(part2, B * d.nblk2, p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, p->bn2_nbt,
+                                                      ws + w.stat2, 1e-5f, 0.1f);
+    else
+        bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, ws + w.stat2, 1e-5f);
+    GNBV_LAUNCH_CHECK("bn2 statistics");
+    const int64_t tot2 = (int64_t)B * d.flat2;
+    bn_relu_apply_kernel<<<(unsigned)ceil_div(tot2, 256), 256, 0, stream>>>(ws + w.y2, ws + w.stat2, ws + w.act2, tot2, d.P2);
+    GNBV_LAUNCH_CHECK("bn_relu_apply_kernel");
+    // Linear(16*G2^3, 256)+ReLU -> cat[:, 256:512]
+    relu_ep.bias = p->grid_fc_b;
+    rc = launch_gemm(ws + w.act2, d.flat2, 1, p->grid_fc_w, 1, d.flat2, ws + w.cat + d.HID, 2 * d.HID, B, d.HID, (int)d.flat2,
+                     relu_ep, ws + w.gemm, stream);
+    if (rc) return rc;
+    // fuse: Linear(512,256)+ReLU -> features
+    relu_ep.bias = p->out_fc_b;
+    return launch_gemm(ws + w.cat, 2 * d.HID, 1, p->out_fc_w, 1, 2 * d.HID, features, d.FEAT, B, d.FEAT, 2 * d.HID, relu_ep,
+                       ws + w.gemm, stream);
+}
+
+extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride, int batch,
+                                     int grid_size, int state_dim, int training, const float* features,
+                                     const float* dfeatures, const gnbv_encoder_grads* gr, void* workspace,
+                                     size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    GNBV_REQUIRE(p && obs && features && dfeatures && gr && workspace, "gnbv_encoder_backward: null pointer argument");
+    GNBV_REQUIRE(gr->conv1_w && gr->conv1_b && gr->bn1_w && gr->bn1_b && gr->conv2_w && gr->conv2_b && gr->bn2_w && gr->bn2_b &&
+                     gr->grid_fc_w && gr->grid_fc_b && gr->act_fc1_w && gr->act_fc1_b && gr->act_fc2_w && gr->act_fc2_b &&
+                     gr->out_fc_w && gr->out_fc_b,
+                 "gnbv_encoder_backward: null gradient pointer");
+    EncDims d = make_dims(batch, grid_size, state_dim);
+    EncWs w = make_ws(d, true);
+    GNBV_REQUIRE(workspace_bytes >= w.total * 4, "gnbv_encoder_backward: workspace %zu B < %zu B (allocate with with_backward=1)",
+                 workspace_bytes, w.total * 4);
+    float* ws = reinterpret_cast<float*>(workspace);
+    const int B = batch, H = d.HID;
+    GemmEpilogue none;
+    int rc;
+    auto blocks = [](int64_t n) { return (unsigned)ceil_div(n, 256); };
+    // ---- fuse layer: features = relu(cat W^T + b)
+    relu_mask_kernel<<<blocks((int64_t)B * d.FEAT), 256, 0, stream>>>(dfeatures, d.FEAT, ws + w.dz, d.FEAT, features, d.FEAT, B, d.FEAT);
+    GNBV_LAUNCH_CHECK("relu_mask_kernel");
+    rc = launch_gemm(ws + w.dz, 1, d.FEAT, ws + w.cat, 2 * H, 1, gr->out_fc_w, 2 * H, d.FEAT, 2 * H, B, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    colsum_kernel<<<blocks(d.FEAT), 256, 0, stream>>>(ws + w.dz, d.FEAT, B, d.FEAT, gr->out_fc_b);
+    rc = launch_gemm(ws + w.dz, d.FEAT, 1, p->out_fc_w, 2 * H, 1, ws + w.dcat, 2 * H, B, 2 * H, d.FEAT, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    relu_mask_kernel<<<blocks((int64_t)B * 2 * H), 256, 0, stream>>>(ws + w.dcat, 2 * H, ws + w.dcat, 2 * H, ws + w.cat, 2 * H, B, 2 * H);
+    // ---- action branch
+    rc = launch_gemm(ws + w.dcat, 1, 2 * H, ws + w.h1, H, 1, gr->act_fc2_w, H, H, H, B, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dcat, 2 * H, B, H, gr->act_fc2_b);
+    rc = launch_gemm(ws + w.dcat, 2 * H, 1, p->act_fc2_w, H, 1, ws + w.dh1, H, B, H, H, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    relu_mask_kernel<<<blocks((int64_t)B * H), 256, 0, stream>>>(ws + w.dh1, H, ws + w.dh1, H, ws + w.h1, H, B, H);
+    rc = launch_gemm(ws + w.dh1, 1, H, ws + w.pe, 4 * d.S, 1, gr->act_fc1_w, 4 * d.S, H, 4 * d.S, B, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dh1, H, B, H, gr->act_fc1_b);
+    // ---- grid branch: Linear
+    const float* dcat_g = ws + w.dcat + H;
+    rc = launch_gemm(dcat_g, 1, 2 * H, ws + w.act2, d.flat2, 1, gr->grid_fc_w, d.flat2, H, (int)d.flat2, B, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    colsum_kernel<<<blocks(H), 256, 0, stream>>>(dcat_g, 2 * H, B, H, gr->grid_fc_b);
+    rc = launch_gemm(dcat_g, 2 * H, 1, p->grid_fc_w, d.flat2, 1, ws + w.dact2, d.flat2, B, (int)d.flat2, H, none, ws + w.gemm, stream);
+    if (rc) return rc;
+    GNBV_LAUNCH_CHECK("linear backward");
+    // ---- BN2 + ReLU backward
+    bn2_bwd_reduce_kernel<<<dim3(C1, B), 256, 0, stream>>>(ws + w.dact2, ws + w.act2, ws + w.y2, ws + w.stat2, ws + w.bn2part, d.P2);
+    bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bn2part, B, 2 * C1, 0, (double)B * d.P2, gr->bn2_w, gr->bn2_b,
+                                                      ws + w.coef2, training ? 0 : 1);
+    bn2_bwd_apply_kernel<<<dim3((unsigned)ceil_div(d.P2, 256), B), 256, 0, stream>>>(ws + w.dact2, ws + w.act2, ws + w.y2,
+                                                                                      ws + w.stat2, ws + w.coef2, ws + w.dy2cl, d.P2);
+    GNBV_LAUNCH_CHECK("bn2 backward");
+    // ---- conv2 backward
+    const size_t smem_wg2 = 3 * (size_t)WG2_REC * 4;
+    GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
+    conv2_wgrad_kernel<<<w.nblk_wg2, WG2_THREADS, smem_wg2, stream>>>(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, d.G1,
+                                                                       d.G2, (int64_t)B * d.P2);
+    GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
+    reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
+                                                                gr->conv2_b);
+    conv2_dgrad_kernel<<<dim3(w.nblk_dg, B), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1,
+                                                                        ws + w.bpart1, d.G1, d.G2);
+    GNBV_LAUNCH_CHECK("conv2_dgrad_kernel");
+    bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bpart1, B * w.nblk_dg, 2 * C1, 1, (double)B * d.P1, gr->bn1_w, gr->bn1_b,
+                                                      ws + w.coef1, training ? 0 : 1);
+    // ---- conv1 backward (weights only: the input is data)
+    conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
+                                                                ws + w.coef1, ws + w.wg1part, d.G, d.G1, (int64_t)B * d.P1);
+    GNBV_LAUNCH_CHECK("conv1_wgrad_kernel");
+    reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, w.nblk_wg1, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
+    GNBV_LAUNCH_CHECK("reduce_records_kernel");
+    return GNBV_OK;
+}

@@ -133,3 +133,16 @@ def gae(rewards, values, episode_starts, last_values, dones, gamma, gae_lambda, 
                              float(gamma), float(gae_lambda), T, N, _ptr(advantages, torch.float32, "advantages", (T, N)),
                              _ptr(returns, torch.float32, "returns", (T, N)), _stream())
     _lib.check(rc, "gnbv_gae")
+
+
+def sgemm(A, a_strides, B, b_strides, C, M, N, K, bias=None, relu=False, ldc=None):
+    """gnbv_sgemm: C[M,N] = relu?(A*B + bias); a_strides = (stride_m, stride_k) of A, b_strides = (stride_k, stride_n) of B
+    in elements."""
+    L = _lib.lib()
+    nbytes = L.gnbv_sgemm_workspace_bytes(M, N, K)
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=C.device)
+    rc = L.gnbv_sgemm(_ptr(A, torch.float32, "A"), a_strides[0], a_strides[1], _ptr(B, torch.float32, "B"), b_strides[0],
+                      b_strides[1], _ptr(C, torch.float32, "C"), N if ldc is None else ldc, M, N, K,
+                      _ptr(bias, torch.float32, "bias"), int(relu), ws.data_ptr() if nbytes else None, nbytes, _stream())
+    _lib.check(rc, "gnbv_sgemm")
+    return C

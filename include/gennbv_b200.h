@@ -147,6 +147,105 @@ int gnbv_reset_envs(uint8_t* reset_buf, float* prob_grid, float* scanned_gt, flo
                     const float* init_pose, const int64_t* init_action, int num_envs, int grid_size, int hist_len,
                     int pose_dim, int rgb_frames, int rgb_h, int rgb_w, int clear_reset_buf, void* stream);
 
+/* ---- Hybrid_Encoder (gennbv/network/hybrid_encoder.py:12-91) ---- */
+
+/* Device pointers of the encoder parameters, in the reference's state_dict order / shapes:
+ *   features_extractor.naive_encoder_grid.0.{weight [16,1,3,3,3], bias [16]}           conv1_w, conv1_b
+ *   features_extractor.naive_encoder_grid.1.{weight, bias, running_mean, running_var [16], num_batches_tracked i64}
+ *   features_extractor.naive_encoder_grid.3.{weight [16,16,3,3,3], bias [16]}          conv2_w, conv2_b
+ *   features_extractor.naive_encoder_grid.4.{...}                                      bn2_*
+ *   features_extractor.output_layer_grid.0.{weight [256, 16*G2^3], bias [256]}         grid_fc_w, grid_fc_b
+ *   features_extractor.naive_encoder_action.0.{weight [256, 4*state_dim], bias}        act_fc1_w, act_fc1_b
+ *   features_extractor.naive_encoder_action.2.{weight [256,256], bias}                 act_fc2_w, act_fc2_b
+ *   features_extractor.output_layer.0.{weight [256,512], bias}                         out_fc_w, out_fc_b
+ * Running statistics are updated in place by a training-mode forward (momentum 0.1), as nn.BatchNorm3d does. */
+typedef struct gnbv_encoder_params {
+    const float *conv1_w, *conv1_b, *bn1_w, *bn1_b;
+    float *bn1_rm, *bn1_rv;
+    int64_t* bn1_nbt;
+    const float *conv2_w, *conv2_b, *bn2_w, *bn2_b;
+    float *bn2_rm, *bn2_rv;
+    int64_t* bn2_nbt;
+    const float *grid_fc_w, *grid_fc_b, *act_fc1_w, *act_fc1_b, *act_fc2_w, *act_fc2_b, *out_fc_w, *out_fc_b;
+} gnbv_encoder_params;
+
+/* Workspace (bytes) for a forward (with_backward = 0) or forward + backward (1) of `batch` rows. */
+size_t gnbv_encoder_workspace_bytes(int batch, int grid_size, int state_dim, int with_backward);
+
+/* Hybrid_Encoder.forward (hybrid_encoder.py:69-91), generalised from the hard-coded 20^3 grid to any G:
+ *   obs row n = obs + n*obs_row_stride: [0, state_dim) pose history (state_dim = buffer_size*6), then G^3 tri-class
+ *   grid values; later columns (the rgb frames) are not read, as in the reference.
+ *   training != 0: BatchNorm3d uses batch statistics and updates the running ones (policies.py:206-214);
+ *   features [batch,256] out.  Activations needed by gnbv_encoder_backward stay in `workspace`. */
+int gnbv_encoder_forward(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride, int batch,
+                         int grid_size, int state_dim, int training, float* features, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* Gradient destinations, one per trainable tensor of gnbv_encoder_params (same shapes). */
+typedef struct gnbv_encoder_grads {
+    float *conv1_w, *conv1_b, *bn1_w, *bn1_b, *conv2_w, *conv2_b, *bn2_w, *bn2_b;
+    float *grid_fc_w, *grid_fc_b, *act_fc1_w, *act_fc1_b, *act_fc2_w, *act_fc2_b, *out_fc_w, *out_fc_b;
+} gnbv_encoder_grads;
+
+/* Backward of gnbv_encoder_forward on the same `workspace` (allocated with with_backward = 1 and untouched since the
+ * forward): dfeatures [batch,256] in, every gradient of `grads` overwritten.  `features` is the forward's output
+ * (ReLU mask).  No gradient w.r.t. the observation is produced (it is data).  Replaces autograd through
+ * hybrid_encoder.py:69-91 inside PPO_Grid_Obs.train (ppo_grid_obs.py:272). */
+int gnbv_encoder_backward(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride, int batch,
+                          int grid_size, int state_dim, int training, const float* features, const float* dfeatures,
+                          const gnbv_encoder_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- actor / critic heads + MultiCategorical distribution + PPO loss + optimizer ---- */
+
+/* action_net Linear(256, sum(nvec)) and value_net Linear(256,1) (stable_baselines3/common/policies.py:984,994,
+ * 1007-1011) evaluated as one product: head_w [num_out, feat_dim] holds action_net.weight followed by
+ * value_net.weight, head_b [num_out] likewise; out [batch, num_out] = logits | value. */
+int gnbv_policy_heads_forward(const float* features, const float* head_w, const float* head_b, float* out,
+                              int batch, int feat_dim, int num_out, void* stream);
+
+/* MultiCategoricalDistribution (stable_baselines3/common/distributions.py:299-352) over logits rows split by
+ * nvec (host array, num_sub entries):
+ *   evaluate : log_prob [B] = sum_k log softmax_k[a_k], entropy [B] = sum_k H_k  (either output may be NULL)
+ *   sample   : actions [B,num_sub] i64 ~ Categorical (Gumbel-max, Philox(seed, offset)) or the mode if deterministic;
+ *              log_prob [B] of the drawn actions (may be NULL)
+ *   backward : dlogits [B, sum(nvec)] from per-row gradients w.r.t. log_prob and entropy. */
+int gnbv_multicategorical_evaluate(const float* logits, int64_t logits_row_stride, const int* nvec, int num_sub,
+                                   const int64_t* actions, float* log_prob, float* entropy, int batch, void* stream);
+int gnbv_multicategorical_sample(const float* logits, int64_t logits_row_stride, const int* nvec, int num_sub,
+                                 uint64_t seed, uint64_t offset, int deterministic, int64_t* actions, float* log_prob,
+                                 int batch, void* stream);
+int gnbv_multicategorical_backward(const float* logits, int64_t logits_row_stride, const int* nvec, int num_sub,
+                                   const int64_t* actions, const float* grad_log_prob, const float* grad_entropy,
+                                   float* dlogits, int64_t dlogits_row_stride, int batch, void* stream);
+
+/* The loss lines of PPO_Grid_Obs.train (stable_baselines3/ppo/ppo_grid_obs.py:213-262) on one minibatch, forward and
+ * backward in one launch: advantage normalisation (unbiased std + 1e-8), clipped surrogate, clipped value loss
+ * (clip_range_vf < 0 disables the clipping), entropy bonus, loss = pg_coef*pg + ent_coef*ent + vf_coef*vf
+ * (pg_coef = 10 in the reference, :253), approx_kl and clip_fraction.
+ *   scalars [8] out: loss, policy_loss, value_loss, entropy_loss, approx_kl, clip_fraction, adv_mean, adv_std
+ *   grad_log_prob / grad_entropy / grad_values [B] out: d loss / d (log_prob, entropy, values). */
+int gnbv_ppo_loss(const float* log_prob, const float* entropy, const float* values, const float* old_values,
+                  const float* old_log_prob, const float* advantages, const float* returns, int batch,
+                  double clip_range, double clip_range_vf, double ent_coef, double vf_coef, double pg_coef,
+                  int normalize_advantage, float* scalars, float* grad_log_prob, float* grad_entropy,
+                  float* grad_values, void* stream);
+
+/* th.nn.utils.clip_grad_norm_ + th.optim.Adam step (ppo_grid_obs.py:271-275; Adam eps 1e-5, policies.py:855) on flat
+ * fp32 buffers.  gnbv_grad_norm writes workspace[0] = ||g||_2 and workspace[1] = min(1, max_norm / (norm + 1e-6));
+ * gnbv_adam_step multiplies the gradient by workspace[1] (if clip_workspace != NULL) and by grad_scale. */
+size_t gnbv_clip_adam_workspace_bytes(void);
+int gnbv_grad_norm(const float* grads, int64_t n, double max_norm, float* workspace, void* stream);
+int gnbv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   const float* clip_workspace, double lr, double beta1, double beta2, double eps, int64_t step,
+                   double grad_scale, void* stream);
+
+/* Bare fp32 GEMM on device pointers: C[M,N] = relu?(A*B + bias), element strides (see gennbv_b200/csrc/gemm.cuh);
+ * replaces the cuBLAS calls behind nn.Linear (hybrid_encoder.py:39-54; policies.py:984,994). */
+size_t gnbv_sgemm_workspace_bytes(int M, int N, int K);
+int gnbv_sgemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* C,
+               int64_t ldc, int M, int N, int K, const float* bias, int relu, float* workspace, size_t workspace_bytes,
+               void* stream);
+
 /* TensorRolloutBuffer_Grid_Obs.compute_returns_and_advantage  (stable_baselines3/common/buffers.py:706-724)
  *   rewards, values [T,N] f32; episode_starts [T,N] u8; last_values [N] f32; dones [N] u8
  *   advantages, returns [T,N] f32 out.  gamma / gae_lambda are the Python doubles of the buffer. */

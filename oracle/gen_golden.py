@@ -125,5 +125,79 @@ def main():
     rollout("env_g20_long", N=3, H=40, W=56, G=20, S=2, T=40, max_episode_length=100, seed=5)
 
 
+
+
+# ------------------------------------------------------------------------------------------------ policy goldens
+def policy_golden(name="policy_g20", seed=7):
+    """Outputs of the reference's own Hybrid_Encoder / ActorCriticPolicy_Train_Eval / PPO loss lines at the
+    reference-native 20^3 grid, on observations taken from the env_g20_long roll-out, with generator-seeded weights
+    (oracle/encoder_ref.py::seeded_state_dict -- reproducible anywhere without the reference)."""
+    import ref_loader
+    import encoder_ref
+    ref = ref_loader.load_reference()
+    from gym import spaces
+    d = np.load(os.path.join(GOLDEN_DIR, "env_g20_long.npz"))
+    N, G = int(d["meta"][0]), int(d["meta"][3])
+    rows = []
+    for t in (0, 3, 9, 20, 33, 40):
+        rows.append(np.concatenate([d["state"][t].reshape(N, -1), d["tri"][t].reshape(N, -1).astype(np.float32),
+                                    d["state_rgb"][t].reshape(N, -1)], 1))
+    obs = torch.from_numpy(np.concatenate(rows, 0))                      # [18, 16792]
+    B, D = obs.shape
+    obs_space = spaces.Box(low=-np.inf, high=np.inf, shape=(D,), dtype=np.float32)
+    act_space = spaces.MultiDiscrete([81, 81, 51, 1, 13, 13])
+    kwargs = dict(encoder_param={"hidden_shapes": [256, 256], "visual_dim": 256},
+                  net_param={"transformer_params": [[1, 256], [1, 256]], "append_hidden_shapes": [256, 256]},
+                  state_input_shape=(600,), visual_input_shape=(100, 48, 48))
+    policy = ref.policies.ActorCriticPolicy_Train_Eval(obs_space, act_space, lambda _: 1e-4, net_arch=[],
+                                                       features_extractor_class=ref.encoder.Hybrid_Encoder,
+                                                       features_extractor_kwargs=kwargs)
+    mirror = encoder_ref.PolicyRef(G, 600)
+    sd = encoder_ref.seeded_state_dict(mirror, seed)
+    policy.load_state_dict(sd)
+    g = torch.Generator().manual_seed(seed + 1)
+    actions = torch.stack([torch.randint(0, n, (B,), generator=g) for n in (81, 81, 51, 1, 13, 13)], 1)
+    out = {"obs_rows": np.array([0, 3, 9, 20, 33, 40]), "actions": actions.numpy(), "seed": np.array(seed)}
+    policy.set_training_mode(False)
+    with torch.no_grad():
+        out["features_eval"] = policy.extract_features(obs).numpy()
+        v, lp, ent = policy.evaluate_actions(obs, actions)
+        out["values_eval"], out["log_prob_eval"], out["entropy_eval"] = v.numpy(), lp.numpy(), ent.numpy()
+    policy.set_training_mode(True)
+    old_v = torch.randn(B, generator=g) * 0.5
+    old_lp = lp.detach() + 0.3 * torch.randn(B, generator=g)
+    adv = torch.randn(B, generator=g) * 2 + 0.3
+    ret = torch.randn(B, generator=g)
+    v, lp, ent = policy.evaluate_actions(obs, actions)
+    out["features_train"] = policy.extract_features(obs).detach().numpy()      # second BN update; recorded below after it
+    loss, parts = encoder_ref.ppo_loss(v, lp, ent, old_v, old_lp, adv, ret)
+    policy.optimizer.zero_grad()
+    loss.backward()
+    out.update(values_train=v.detach().numpy(), log_prob_train=lp.detach().numpy(), entropy_train=ent.detach().numpy(),
+               old_values=old_v.numpy(), old_log_prob=old_lp.numpy(), advantages=adv.numpy(), returns=ret.numpy(),
+               loss=loss.detach().numpy(), **{k: x.detach().numpy() for k, x in parts.items()})
+    for k, p in policy.named_parameters():
+        out["grad." + k] = p.grad.numpy()
+    for k, b in policy.named_buffers():
+        out["buf." + k] = b.detach().numpy().copy()
+    total_norm = torch.nn.utils.clip_grad_norm_(policy.parameters(), 1.0)
+    policy.optimizer.step()
+    out["grad_norm"] = total_norm.numpy()
+    for k, p in policy.named_parameters():
+        out["new." + k] = p.detach().numpy()
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    keep = {k: v for k, v in out.items() if not (k.startswith("grad.") or k.startswith("new.")) or v.size <= 4096}
+    # large tensors: keep a strided sample + norm (fixtures stay small)
+    for k, v in out.items():
+        if k not in keep:
+            flat = v.reshape(-1)
+            keep[k + ".sample"] = flat[:: max(1, flat.size // 2048)][:2048].copy()
+            keep[k + ".norm"] = np.array(np.linalg.norm(flat.astype(np.float64)))
+    np.savez_compressed(path, **keep)
+    print(f"{path}: {os.path.getsize(path) / 1e6:.2f} MB; loss={float(loss):.6f} grad_norm={float(total_norm):.4f}")
+
+
 if __name__ == "__main__":
-    main()
+    if "--policy" not in sys.argv:
+        main()
+    policy_golden()

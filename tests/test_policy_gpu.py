@@ -1,0 +1,199 @@
+"""GPU parity tests of the policy network kernels (encoder forward/backward, heads, MultiCategorical, PPO loss,
+clip + Adam) against (a) goldens produced by the reference's own modules at the native 20^3 grid and (b) the plain
+PyTorch fp32 restatement (oracle/encoder_ref.py) at other sizes.  Tolerance: <= 1e-4 relative (BASELINE.json)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import encoder_ref
+from gennbv_b200 import _lib, ops
+from gennbv_b200.policy import ActorCriticPolicy_Train_Eval
+from gennbv_b200.spaces import Box, MultiDiscrete
+from helpers import GOLDEN_DIR
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL = 1e-4
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def make_policy(G, seed, state_dim=600):
+    D = state_dim + G ** 3 + 2 * 64 * 64
+    kwargs = dict(encoder_param={"hidden_shapes": [256, 256], "visual_dim": 256},
+                  net_param={"transformer_params": [[1, 256], [1, 256]], "append_hidden_shapes": [256, 256]},
+                  state_input_shape=(state_dim,), visual_input_shape=(100, 48, 48))
+    pol = ActorCriticPolicy_Train_Eval(Box(-np.inf, np.inf, (D,), np.float32), MultiDiscrete([81, 81, 51, 1, 13, 13]),
+                                       lambda _: 1e-4, net_arch=[], features_extractor_kwargs=kwargs, device=DEV)
+    ref = encoder_ref.PolicyRef(G, state_dim)
+    sd = encoder_ref.seeded_state_dict(ref, seed)
+    ref.load_state_dict(sd)
+    pol.load_state_dict(sd)
+    return pol, ref, D
+
+
+def golden_obs():
+    d = np.load(os.path.join(GOLDEN_DIR, "env_g20_long.npz"))
+    N = int(d["meta"][0])
+    rows = [np.concatenate([d["state"][t].reshape(N, -1), d["tri"][t].reshape(N, -1).astype(np.float32),
+                            d["state_rgb"][t].reshape(N, -1)], 1) for t in (0, 3, 9, 20, 33, 40)]
+    return torch.from_numpy(np.concatenate(rows, 0))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 2400), (256, 241, 256), (7, 5, 3), (130, 67, 54000), (256, 54000, 128), (128, 1000, 256)])
+def test_sgemm_modes(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A, Bm = torch.randn(M, K, generator=g), torch.randn(K, N, generator=g)
+    want = (A.double() @ Bm.double())
+    Ad, Bd = A.to(DEV), Bm.to(DEV)
+    At, Bt = A.t().contiguous().to(DEV), Bm.t().contiguous().to(DEV)
+    scale = float(want.abs().max())
+    for (a, sa), (b, sb) in [((Ad, (K, 1)), (Bd, (N, 1))), ((Ad, (K, 1)), (Bt, (1, K))), ((At, (1, M)), (Bd, (N, 1))),
+                             ((At, (1, M)), (Bt, (1, K)))]:
+        C = torch.full((M, N), float("nan"), device=DEV)
+        ops.sgemm(a, sa, b, sb, C, M, N, K)
+        assert float((C.cpu().double() - want).abs().max()) / scale < 2e-6
+    bias = torch.randn(N, generator=g)
+    C = torch.empty(M, N, device=DEV)
+    ops.sgemm(Ad, (K, 1), Bd, (N, 1), C, M, N, K, bias=bias.to(DEV), relu=True)
+    assert float((C.cpu().double() - torch.relu(want + bias.double())).abs().max()) / scale < 2e-6
+
+
+def test_policy_matches_reference_golden_g20():
+    """Forward (eval + train BN), log_prob / entropy / values, PPO loss, every gradient, clip norm and the Adam step
+    against tests/golden/policy_g20.npz (written by the reference's own modules)."""
+    gd = np.load(os.path.join(GOLDEN_DIR, "policy_g20.npz"))
+    pol, _, D = make_policy(20, int(gd["seed"]))
+    obs = golden_obs().to(DEV)
+    actions = torch.from_numpy(gd["actions"]).to(DEV)
+    pol.set_training_mode(False)
+    with torch.no_grad():
+        assert rel_err(pol.extract_features(obs).cpu(), gd["features_eval"]) < RTOL
+        v, lp, ent = pol.evaluate_actions(obs, actions)
+    for got, key in ((v, "values_eval"), (lp, "log_prob_eval"), (ent, "entropy_eval")):
+        assert rel_err(got.cpu(), gd[key]) < RTOL, key
+    pol.set_training_mode(True)
+    v, lp, ent = pol.evaluate_actions(obs, actions)
+    for got, key in ((v, "values_train"), (lp, "log_prob_train"), (ent, "entropy_train")):
+        assert rel_err(got.detach().cpu(), gd[key]) < RTOL, key
+    with torch.no_grad():
+        assert rel_err(pol.extract_features(obs).cpu(), gd["features_train"]) < RTOL
+    T = lambda k: torch.from_numpy(gd[k]).to(DEV)
+    loss, parts = encoder_ref.ppo_loss(v, lp, ent, T("old_values"), T("old_log_prob"), T("advantages"), T("returns"))
+    assert rel_err(loss.detach().cpu(), gd["loss"]) < RTOL
+    pol.optimizer.zero_grad()
+    loss.backward()
+    for k, p in pol.named_parameters():
+        g = p.grad.detach().cpu().numpy()
+        if "grad." + k in gd.files:
+            assert rel_err(g, gd["grad." + k]) < 2e-4, k
+        else:
+            flat = g.reshape(-1)
+            assert rel_err(flat[:: max(1, flat.size // 2048)][:2048], gd["grad." + k + ".sample"]) < 2e-4, k
+            assert abs(np.linalg.norm(flat.astype(np.float64)) / float(gd["grad." + k + ".norm"]) - 1) < 1e-4, k
+    for k, b in pol.named_buffers():
+        assert rel_err(b.detach().cpu().numpy().astype(np.float64), gd["buf." + k]) < RTOL, k
+    assert int(pol.features_extractor.naive_encoder_grid[1].num_batches_tracked) == 2
+
+
+@pytest.mark.parametrize("G,B,seed", [(20, 9, 1), (32, 5, 2), (64, 3, 3), (21, 4, 4)])
+def test_encoder_forward_backward_vs_torch(G, B, seed):
+    pol, ref, D = make_policy(G, seed)
+    g = torch.Generator().manual_seed(seed)
+    obs = torch.zeros(B, D)
+    obs[:, :600] = torch.randn(B, 600, generator=g) * 3
+    obs[:, 600:600 + G ** 3] = torch.randint(-1, 2, (B, G ** 3), generator=g).float()
+    obs[:, 600 + G ** 3:] = torch.rand(B, 8192, generator=g) * 255
+    wsum = torch.randn(B, 256, generator=g)
+    for training in (False, True):
+        ref.train(training); pol.train(training)
+        ref.zero_grad()
+        f_ref = ref.features_extractor(obs)
+        (f_ref * wsum).sum().backward()
+        enc = pol.features_extractor
+        for p in enc.parameters():
+            p.grad = None
+        f = enc(obs.to(DEV))
+        assert rel_err(f.detach().cpu(), f_ref.detach()) < RTOL, f"features training={training}"
+        (f * wsum.to(DEV)).sum().backward()
+        ref_grads = dict(ref.features_extractor.named_parameters())
+        for k, p in enc.named_parameters():
+            assert rel_err(p.grad.cpu(), ref_grads[k].grad) < 2e-4, f"grad {k} training={training}"
+        if training:
+            for k, b in enc.named_buffers():
+                assert rel_err(b.cpu().double(), dict(ref.features_extractor.named_buffers())[k].double()) < RTOL, k
+
+
+def test_multicategorical_sampling_and_mode():
+    pol, ref, D = make_policy(20, 5)
+    obs = golden_obs()[:4].to(DEV)
+    pol.set_training_mode(False)
+    a_det, v, lp = pol(obs, deterministic=True)
+    with torch.no_grad():
+        logits = ref.action_net(ref.features_extractor.eval()(obs.cpu()))
+    want = torch.stack([s.argmax(1) for s in torch.split(logits, ref.nvec, dim=1)], 1)
+    assert torch.equal(a_det.cpu(), want)
+    # log_prob returned with the sample equals evaluate_actions of that sample
+    a, v, lp = pol(obs)
+    _, lp2, _ = pol.evaluate_actions(obs, a)
+    assert rel_err(lp.cpu(), lp2.detach().cpu()) < 1e-5
+    assert int(a.min()) >= 0 and bool((a.cpu() < torch.tensor(ref.nvec)).all())
+    # distributional check: empirical frequencies of the 13-way yaw head over 4000 draws of one row
+    big = obs[:1].repeat(4000, 1)
+    a, _, _ = pol(big)
+    p = torch.softmax(torch.split(logits[:1], ref.nvec, dim=1)[5], 1)[0]
+    freq = torch.bincount(a[:, 5].cpu(), minlength=13).float() / 4000
+    assert float((freq - p).abs().max()) < 0.04
+    a2, _, _ = pol(big)
+    assert not torch.equal(a, a2), "successive calls must draw fresh samples"
+
+
+def test_ppo_loss_kernel_vs_autograd():
+    g = torch.Generator().manual_seed(0)
+    B = 128
+    lp = (torch.randn(B, generator=g) * 0.3 - 8).requires_grad_()
+    ent = (torch.rand(B, generator=g) * 3 + 5).requires_grad_()
+    v = torch.randn(B, generator=g).requires_grad_()
+    old_v, old_lp = v.detach() + 0.3 * torch.randn(B, generator=g), lp.detach() + 0.25 * torch.randn(B, generator=g)
+    adv, ret = torch.randn(B, generator=g) * 2, torch.randn(B, generator=g)
+    loss, parts = encoder_ref.ppo_loss(v, lp, ent, old_v, old_lp, adv, ret)
+    loss.backward()
+    d = lambda t: t.detach().to(DEV).contiguous()
+    sc = torch.zeros(8, device=DEV)
+    glp, ge, gv = (torch.empty(B, device=DEV) for _ in range(3))
+    rc = _lib.lib().gnbv_ppo_loss(d(lp).data_ptr(), d(ent).data_ptr(), d(v).data_ptr(), d(old_v).data_ptr(), d(old_lp).data_ptr(),
+                                  d(adv).data_ptr(), d(ret).data_ptr(), B, 0.2, 0.2, 0.01, 0.8, 10.0, 1, sc.data_ptr(),
+                                  glp.data_ptr(), ge.data_ptr(), gv.data_ptr(), ops._stream())
+    _lib.check(rc, "gnbv_ppo_loss")
+    sc = sc.cpu()
+    for i, k in enumerate(["policy_loss", "value_loss", "entropy_loss", "approx_kl", "clip_fraction"]):
+        assert abs(float(sc[i + 1]) - float(parts[k])) <= 1e-5 * max(1.0, abs(float(parts[k]))), k
+    assert abs(float(sc[0]) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert rel_err(glp.cpu(), lp.grad) < 1e-5 and rel_err(ge.cpu(), ent.grad) < 1e-6 and rel_err(gv.cpu(), v.grad) < 1e-5
+
+
+def test_clip_and_adam_match_torch():
+    g = torch.Generator().manual_seed(1)
+    n = 1_143_553
+    p0, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 0.01
+    p_ref = p0.clone().requires_grad_()
+    opt = torch.optim.Adam([p_ref], lr=1e-4, eps=1e-5)
+    p, m, v = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    L = _lib.lib()
+    ws = torch.zeros(L.gnbv_clip_adam_workspace_bytes() // 4, device=DEV)
+    for step in range(1, 4):
+        grad = gr * step
+        p_ref.grad = grad.clone()
+        norm = torch.nn.utils.clip_grad_norm_([p_ref], 1.0)
+        opt.step()
+        gd = grad.to(DEV)
+        _lib.check(L.gnbv_grad_norm(gd.data_ptr(), n, 1.0, ws.data_ptr(), ops._stream()), "gnbv_grad_norm")
+        _lib.check(L.gnbv_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, ws.data_ptr(), 1e-4, 0.9, 0.999,
+                                    1e-5, step, 1.0, ops._stream()), "gnbv_adam_step")
+        assert abs(float(ws[0]) / float(norm) - 1) < 1e-5
+        assert rel_err((p.cpu() - p0), (p_ref.detach() - p0)) < 1e-4
