@@ -50,9 +50,9 @@ SIGNATURES = {
                                                                                        c_int, c_void_p]),
     "gnbv_reset_envs": (c_int, [c_void_p] * 11 + [c_int] * 8 + [c_void_p]),
     "gnbv_encoder_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "gnbv_encoder_forward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_int, c_int, c_int, c_int,
+    "gnbv_encoder_forward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
-    "gnbv_encoder_backward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_int, c_int, c_int, c_int,
+    "gnbv_encoder_backward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_void_p]),
     "gnbv_policy_heads_forward": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "gnbv_multicategorical_evaluate": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_int), c_int, c_void_p, c_void_p,

@@ -71,13 +71,14 @@ __device__ __forceinline__ void block_stats(const float (&acc)[NV][C1], int nval
 // ------------------------------------------------------------------------------------------------ posenc
 // positional_encoding (hybrid_encoder.py:56-67): per pose p[6] -> [sin(p_i * f), ...] then [cos(...)], f in {1,2},
 // order (i major, f minor); 24 values per pose.
-__global__ void posenc_kernel(const float* __restrict__ obs, int64_t obs_stride, float* __restrict__ pe, int B, int S) {
+__global__ void posenc_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows,
+                              float* __restrict__ pe, int B, int S) {
     // S = buffer_size * 6 state values per row; output [B, 4*S]
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)B * S) return;
     int b = (int)(idx / S), s = (int)(idx - (int64_t)b * S);
     int pose = s / 6, i = s - pose * 6;
-    float x = obs[(int64_t)b * obs_stride + s];
+    float x = obs[(rows ? rows[b] : (int64_t)b) * obs_stride + s];
     float* o = pe + (int64_t)b * 4 * S + pose * 24;
     float x1 = x * 1.0f, x2 = x * 2.0f;
     o[2 * i] = sinf(x1); o[2 * i + 1] = sinf(x2);
@@ -88,7 +89,8 @@ __global__ void posenc_kernel(const float* __restrict__ obs, int64_t obs_stride,
 // Conv3d(1,16,3,stride 2) on the grid columns of the observation.  y1 [B, G1^3, 16] (pre-BN, channels-last).
 // Per-block partial (sum, sumsq) per channel -> part[blk][32] when stats != nullptr.
 __global__ void __launch_bounds__(CONV1_THREADS)
-conv1_fwd_kernel(const float* __restrict__ obs, int64_t obs_stride, int64_t grid_off, const float* __restrict__ w,
+conv1_fwd_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
+                 const float* __restrict__ w,
                  const float* __restrict__ bias, float* __restrict__ y1, float* __restrict__ part, int G, int G1) {
     __shared__ __align__(16) float ws[TAPS][C1];
     __shared__ float bs[C1];
@@ -108,7 +110,7 @@ conv1_fwd_kernel(const float* __restrict__ obs, int64_t obs_stride, int64_t grid
     if (valid) {
         int z1 = p % G1, t = p / G1;
         int yy = t % G1, xx = t / G1;
-        const float* in = obs + (int64_t)b * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
+        const float* in = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
 #pragma unroll
         for (int c = 0; c < C1; ++c) acc[c] = bs[c];
 #pragma unroll
@@ -566,7 +568,8 @@ constexpr int WG1_THREADS = 256;
 constexpr int WG1_POS_PER_STREAM = 64;
 constexpr int WG1_REC = C1 * TAPS + C1;
 __global__ void __launch_bounds__(WG1_THREADS)
-conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, int64_t grid_off, const float* __restrict__ g1,
+conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
+                   const float* __restrict__ g1,
                    const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ coef,
                    float* __restrict__ part, int G, int G1, int64_t total_pos) {
     __shared__ float red[WG1_THREADS / 32][WG1_REC];
@@ -598,7 +601,7 @@ conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, int64_t gr
             dy[q] = a1[q] * (g4[q] - k1[q] - ((y4[q] - mean[q]) * invstd[q]) * k2[q]);
             if (th == 0) dbs[q] += dy[q];
         }
-        const float* in = obs + (int64_t)b * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
+        const float* in = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
 #pragma unroll
         for (int tt = 0; tt < 14; ++tt) {
             const int tap = 14 * th + tt;
@@ -745,8 +748,9 @@ extern "C" size_t gnbv_encoder_workspace_bytes(int batch, int grid_size, int sta
     return make_ws(d, with_backward != 0).total * 4 + 256;
 }
 
-extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride, int batch,
-                                    int grid_size, int state_dim, int training, float* features, void* workspace,
+extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
+                                    const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                                    float* features, void* workspace,
                                     size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GNBV_REQUIRE(p && obs && features && workspace, "gnbv_encoder_forward: null pointer argument");
@@ -763,15 +767,14 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     EncWs w = make_ws(d, false);
     GNBV_REQUIRE(workspace_bytes >= w.total * 4, "gnbv_encoder_forward: workspace %zu B < %zu B", workspace_bytes, w.total * 4);
     if (workspace_bytes >= make_ws(d, true).total * 4) w = make_ws(d, true);
-    GNBV_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)obs & 15) == 0 && obs_row_stride % 4 == 0 && state_dim % 4 == 0,
-                 "gnbv_encoder_forward: workspace must be 256 B aligned, obs rows 16 B aligned");
+    GNBV_REQUIRE(((uintptr_t)workspace & 255) == 0, "gnbv_encoder_forward: workspace must be 256 B aligned");
     float* ws = reinterpret_cast<float*>(workspace);
     const int B = batch;
     GemmEpilogue relu_ep;
     relu_ep.relu = 1;
     int rc;
     // ---- action branch: positional encoding -> Linear(4S,256)+ReLU -> Linear(256,256)+ReLU (written into cat[:, :256])
-    posenc_kernel<<<(unsigned)ceil_div((int64_t)B * d.S, 256), 256, 0, stream>>>(obs, obs_row_stride, ws + w.pe, B, d.S);
+    posenc_kernel<<<(unsigned)ceil_div((int64_t)B * d.S, 256), 256, 0, stream>>>(obs, obs_row_stride, row_index, ws + w.pe, B, d.S);
     GNBV_LAUNCH_CHECK("posenc_kernel");
     relu_ep.bias = p->act_fc1_b;
     rc = launch_gemm(ws + w.pe, 4 * d.S, 1, p->act_fc1_w, 1, 4 * d.S, ws + w.h1, d.HID, B, d.HID, 4 * d.S, relu_ep, ws + w.gemm, stream);
@@ -781,7 +784,7 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     if (rc) return rc;
     // ---- grid branch
     float* part1 = training ? ws + w.part1 : nullptr;
-    conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, state_dim, p->conv1_w, p->conv1_b,
+    conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
                                                                       ws + w.y1, part1, d.G, d.G1);
     GNBV_LAUNCH_CHECK("conv1_fwd_kernel");
     if (training)
@@ -814,8 +817,9 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
                        ws + w.gemm, stream);
 }
 
-extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride, int batch,
-                                     int grid_size, int state_dim, int training, const float* features,
+extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
+                                     const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                                     const float* features,
                                      const float* dfeatures, const gnbv_encoder_grads* gr, void* workspace,
                                      size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -881,7 +885,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bpart1, B * w.nblk_dg, 2 * C1, 1, (double)B * d.P1, gr->bn1_w, gr->bn1_b,
                                                       ws + w.coef1, training ? 0 : 1);
     // ---- conv1 backward (weights only: the input is data)
-    conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
+    conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
                                                                 ws + w.coef1, ws + w.wg1part, d.G, d.G1, (int64_t)B * d.P1);
     GNBV_LAUNCH_CHECK("conv1_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, w.nblk_wg1, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);

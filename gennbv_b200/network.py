@@ -29,8 +29,10 @@ def _grid_from_obs_dim(obs_dim, state_dim, rgb_dim):
 class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, obs, enc, *params):
-        feats = enc._run_forward(obs)
+        feats = enc._run_forward(obs, need_bwd=True)     # grad mode is off inside Function.forward: say so explicitly
         ctx.enc, ctx.obs = enc, obs
+        ctx.ws = enc._ws                     # the activations of THIS forward live here until backward
+        enc._busy.add(ctx.ws.data_ptr())
         ctx.batch = obs.shape[0]
         ctx.training = enc.training
         ctx.save_for_backward(feats)
@@ -40,7 +42,8 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, dfeat):
         enc = ctx.enc
         (feats,) = ctx.saved_tensors
-        grads = enc._run_backward(ctx.obs, feats, dfeat.contiguous(), ctx.batch, ctx.training)
+        grads = enc._run_backward(ctx.obs, feats, dfeat.contiguous(), ctx.batch, ctx.training, ctx.ws)
+        enc._busy.discard(ctx.ws.data_ptr())
         return (None, None) + tuple(grads)
 
 
@@ -80,6 +83,7 @@ class Hybrid_Encoder(nn.Module):
         self.output_layer = nn.Sequential(nn.Linear(512, 256), nn.ReLU(inplace=True))
         self._ws_cache = {}
         self._ws = None
+        self._busy = set()                   # workspaces holding activations of a forward whose backward is pending
 
     @property
     def features_dim(self):
@@ -113,12 +117,16 @@ class Hybrid_Encoder(nn.Module):
 
     def _workspace(self, batch, device, with_backward):
         key = (batch, str(device), bool(with_backward))
-        if key not in self._ws_cache:
+        cached = self._ws_cache.get(key)
+        if cached is None or cached.data_ptr() in self._busy:
             n = _lib.lib().gnbv_encoder_workspace_bytes(batch, self.grid_size, self.state_dim, int(with_backward))
             if n == 0:
                 raise RuntimeError("gnbv_encoder_workspace_bytes rejected the sizes")
-            self._ws_cache[key] = torch.empty(n, dtype=torch.uint8, device=device)
-        self._ws = self._ws_cache[key]
+            fresh = torch.empty(n, dtype=torch.uint8, device=device)
+            if cached is None:
+                self._ws_cache[key] = fresh
+            cached = fresh                   # a pending backward owns the cached one: use a private buffer
+        self._ws = cached
         return self._ws
 
     def _check_obs(self, obs):
@@ -130,26 +138,29 @@ class Hybrid_Encoder(nn.Module):
             raise RuntimeError("observation row shorter than state + grid")
         return obs
 
-    def _run_forward(self, obs):
-        B = obs.shape[0]
-        need_bwd = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+    def _run_forward(self, obs, need_bwd=False, row_index=None, training=None, feats=None):
+        """obs [rows, D]; with row_index ([B] i64 on the device) sample b reads obs[row_index[b]] (no gather copy)."""
+        B = obs.shape[0] if row_index is None else row_index.shape[0]
+        training = self.training if training is None else training
         ws = self._workspace(B, obs.device, need_bwd)
-        feats = torch.empty(B, 256, device=obs.device)
+        feats = torch.empty(B, 256, device=obs.device) if feats is None else feats
         p = self._c_params()
-        rc = _lib.lib().gnbv_encoder_forward(ctypes.byref(p), obs.data_ptr(), obs.stride(0), B, self.grid_size,
-                                             self.state_dim, int(self.training), feats.data_ptr(), ws.data_ptr(),
+        rc = _lib.lib().gnbv_encoder_forward(ctypes.byref(p), obs.data_ptr(), obs.stride(0),
+                                             None if row_index is None else row_index.data_ptr(), B, self.grid_size,
+                                             self.state_dim, int(training), feats.data_ptr(), ws.data_ptr(),
                                              ws.numel(), ops._stream())
         _lib.check(rc, "gnbv_encoder_forward")
         return feats
 
-    def _run_backward(self, obs, feats, dfeat, batch, ctx_training=True):
-        grads = [torch.empty_like(p) for p in self._param_list()]
+    def _run_backward(self, obs, feats, dfeat, batch, ctx_training=True, ws=None, row_index=None, grads=None):
+        grads = [torch.empty_like(p) for p in self._param_list()] if grads is None else grads
         gp = _lib.EncoderGrads()
         for name, g in zip(_lib.EncoderGrads.FIELDS, grads):
             setattr(gp, name, g.data_ptr())
         p = self._c_params()
-        ws = self._ws
-        rc = _lib.lib().gnbv_encoder_backward(ctypes.byref(p), obs.data_ptr(), obs.stride(0), batch, self.grid_size,
+        ws = self._ws if ws is None else ws
+        rc = _lib.lib().gnbv_encoder_backward(ctypes.byref(p), obs.data_ptr(), obs.stride(0),
+                                              None if row_index is None else row_index.data_ptr(), batch, self.grid_size,
                                               self.state_dim, int(ctx_training), feats.data_ptr(), dfeat.data_ptr(),
                                               ctypes.byref(gp),
                                               ws.data_ptr(), ws.numel(), ops._stream())

@@ -30,7 +30,9 @@ class _HeadsFn(torch.autograd.Function):
     """action_net + value_net + MultiCategorical log_prob / entropy (policies.py:1052-1068; distributions.py:323-337)."""
 
     @staticmethod
-    def forward(ctx, feats, head_w, head_b, actions, policy):
+    def forward(ctx, feats, action_w, action_b, value_w, value_b, actions, policy):
+        # the four head tensors are adjacent views of one [A+1, F] / [A+1] storage (policy.head_w / head_b)
+        head_w, head_b = policy.head_w, policy.head_b
         B, A = feats.shape[0], policy.num_logits
         L = _lib.lib()
         out = torch.empty(B, A + 1, device=feats.device)
@@ -61,7 +63,8 @@ class _HeadsFn(torch.autograd.Function):
         dfeat, dW = torch.empty(B, F, device=feats.device), torch.empty_like(head_w)
         ops.sgemm(dout, (A + 1, 1), head_w, (F, 1), dfeat, B, F, A + 1)                    # dfeat = dout W
         ops.sgemm(dout, (1, A + 1), feats, (F, 1), dW, A + 1, F, B)                        # dW = dout^T feats
-        return dfeat, dW, dout.sum(dim=0), None, None
+        db = dout.sum(dim=0)
+        return dfeat, dW[:A], db[:A], dW[A:], db[A:], None, None
 
 
 class ActorCriticPolicy_Train_Eval(nn.Module):
@@ -130,6 +133,12 @@ class ActorCriticPolicy_Train_Eval(nn.Module):
         self.head_w_grad = self.flat_grads[o_w:o_w + (A + 1) * F].view(A + 1, F)
         self.head_b_grad = self.flat_grads[o_b:o_b + A + 1]
 
+    def encoder_grad_views(self):
+        """Views of the flat gradient arena for the encoder's 16 tensors, in gnbv_encoder_grads order (independent of
+        whatever `p.grad` currently points to)."""
+        enc_params = self.features_extractor._param_list()
+        return [self.flat_grads[o:o + n].view_as(p) for p, (o, n) in zip(enc_params, self._arena)]
+
     def set_training_mode(self, mode):
         self.train(mode)
 
@@ -165,8 +174,9 @@ class ActorCriticPolicy_Train_Eval(nn.Module):
         feats = self.extract_features(obs)
         actions = actions.long().contiguous()
         if torch.is_grad_enabled():
-            return _HeadsFn.apply(feats, self.head_w, self.head_b, actions, self)
-        return _HeadsFn.forward(_NoCtx(), feats, self.head_w, self.head_b, actions, self)
+            return _HeadsFn.apply(feats, self.action_net.weight, self.action_net.bias, self.value_net.weight,
+                                  self.value_net.bias, actions, self)
+        return _HeadsFn.forward(_NoCtx(), feats, None, None, None, None, actions, self)
 
     def predict_values(self, obs):
         """policies.py:1081-1090."""

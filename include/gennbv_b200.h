@@ -175,11 +175,13 @@ size_t gnbv_encoder_workspace_bytes(int batch, int grid_size, int state_dim, int
 /* Hybrid_Encoder.forward (hybrid_encoder.py:69-91), generalised from the hard-coded 20^3 grid to any G:
  *   obs row n = obs + n*obs_row_stride: [0, state_dim) pose history (state_dim = buffer_size*6), then G^3 tri-class
  *   grid values; later columns (the rgb frames) are not read, as in the reference.
+ *   row_index (device, [batch] i64, or NULL): sample b reads row row_index[b] -- a PPO minibatch is consumed straight
+ *   from the rollout buffer without the gather copy of buffers.py:753-762;
  *   training != 0: BatchNorm3d uses batch statistics and updates the running ones (policies.py:206-214);
  *   features [batch,256] out.  Activations needed by gnbv_encoder_backward stay in `workspace`. */
-int gnbv_encoder_forward(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride, int batch,
-                         int grid_size, int state_dim, int training, float* features, void* workspace,
-                         size_t workspace_bytes, void* stream);
+int gnbv_encoder_forward(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride,
+                         const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                         float* features, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Gradient destinations, one per trainable tensor of gnbv_encoder_params (same shapes). */
 typedef struct gnbv_encoder_grads {
@@ -191,9 +193,10 @@ typedef struct gnbv_encoder_grads {
  * forward): dfeatures [batch,256] in, every gradient of `grads` overwritten.  `features` is the forward's output
  * (ReLU mask).  No gradient w.r.t. the observation is produced (it is data).  Replaces autograd through
  * hybrid_encoder.py:69-91 inside PPO_Grid_Obs.train (ppo_grid_obs.py:272). */
-int gnbv_encoder_backward(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride, int batch,
-                          int grid_size, int state_dim, int training, const float* features, const float* dfeatures,
-                          const gnbv_encoder_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+int gnbv_encoder_backward(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride,
+                          const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                          const float* features, const float* dfeatures, const gnbv_encoder_grads* grads,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- actor / critic heads + MultiCategorical distribution + PPO loss + optimizer ---- */
 

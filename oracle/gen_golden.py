@@ -177,14 +177,14 @@ def policy_golden(name="policy_g20", seed=7):
                old_values=old_v.numpy(), old_log_prob=old_lp.numpy(), advantages=adv.numpy(), returns=ret.numpy(),
                loss=loss.detach().numpy(), **{k: x.detach().numpy() for k, x in parts.items()})
     for k, p in policy.named_parameters():
-        out["grad." + k] = p.grad.numpy()
+        out["grad." + k] = p.grad.numpy().copy()      # clip_grad_norm_ below rescales .grad in place
     for k, b in policy.named_buffers():
         out["buf." + k] = b.detach().numpy().copy()
     total_norm = torch.nn.utils.clip_grad_norm_(policy.parameters(), 1.0)
     policy.optimizer.step()
     out["grad_norm"] = total_norm.numpy()
     for k, p in policy.named_parameters():
-        out["new." + k] = p.detach().numpy()
+        out["new." + k] = p.detach().numpy().copy()
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     keep = {k: v for k, v in out.items() if not (k.startswith("grad.") or k.startswith("new.")) or v.size <= 4096}
     # large tensors: keep a strided sample + norm (fixtures stay small)

@@ -23,6 +23,15 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
 
 
+def grad_close(k, got, want, training, scale, rtol=2e-4):
+    """A conv bias followed by train-mode BatchNorm has an exactly-zero gradient: both sides hold rounding noise
+    there, so the comparison is absolute, relative to the layer's weight-gradient scale."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    if training and (k.endswith("naive_encoder_grid.0.bias") or k.endswith("naive_encoder_grid.3.bias")):
+        return float(np.abs(got - want).max()) < rtol * scale
+    return rel_err(got, want) < rtol
+
+
 def make_policy(G, seed, state_dim=600):
     D = state_dim + G ** 3 + 2 * 64 * 64
     kwargs = dict(encoder_param={"hidden_shapes": [256, 256], "visual_dim": 256},
@@ -88,10 +97,11 @@ def test_policy_matches_reference_golden_g20():
     assert rel_err(loss.detach().cpu(), gd["loss"]) < RTOL
     pol.optimizer.zero_grad()
     loss.backward()
+    scale = float(np.abs(gd["grad.features_extractor.naive_encoder_grid.0.weight"]).max())
     for k, p in pol.named_parameters():
         g = p.grad.detach().cpu().numpy()
         if "grad." + k in gd.files:
-            assert rel_err(g, gd["grad." + k]) < 2e-4, k
+            assert grad_close(k, g, gd["grad." + k], True, scale), k
         else:
             flat = g.reshape(-1)
             assert rel_err(flat[:: max(1, flat.size // 2048)][:2048], gd["grad." + k + ".sample"]) < 2e-4, k
@@ -99,6 +109,16 @@ def test_policy_matches_reference_golden_g20():
     for k, b in pol.named_buffers():
         assert rel_err(b.detach().cpu().numpy().astype(np.float64), gd["buf." + k]) < RTOL, k
     assert int(pol.features_extractor.naive_encoder_grid[1].num_batches_tracked) == 2
+    # clip_grad_norm_(1.0) + Adam step of the reference run vs torch's optimizer on our gradients
+    before = {k: p.detach().clone() for k, p in pol.named_parameters()}
+    norm = torch.nn.utils.clip_grad_norm_(pol.parameters(), 1.0)
+    assert abs(float(norm) / float(gd["grad_norm"]) - 1) < RTOL
+    pol.optimizer.step()
+    for k, p in pol.named_parameters():
+        new = p.detach().cpu().numpy()
+        if "new." + k in gd.files:
+            delta_ref = gd["new." + k] - before[k].cpu().numpy()
+            assert float(np.abs((new - before[k].cpu().numpy()) - delta_ref).max()) <= 2e-3 * 1e-4 + 1e-9, k
 
 
 @pytest.mark.parametrize("G,B,seed", [(20, 9, 1), (32, 5, 2), (64, 3, 3), (21, 4, 4)])
@@ -122,8 +142,9 @@ def test_encoder_forward_backward_vs_torch(G, B, seed):
         assert rel_err(f.detach().cpu(), f_ref.detach()) < RTOL, f"features training={training}"
         (f * wsum.to(DEV)).sum().backward()
         ref_grads = dict(ref.features_extractor.named_parameters())
+        scale = float(ref_grads["naive_encoder_grid.3.weight"].grad.abs().max())
         for k, p in enc.named_parameters():
-            assert rel_err(p.grad.cpu(), ref_grads[k].grad) < 2e-4, f"grad {k} training={training}"
+            assert grad_close(k, p.grad.cpu(), ref_grads[k].grad, training, scale), f"grad {k} training={training}"
         if training:
             for k, b in enc.named_buffers():
                 assert rel_err(b.cpu().double(), dict(ref.features_extractor.named_buffers())[k].double()) < RTOL, k
@@ -166,14 +187,14 @@ def test_ppo_loss_kernel_vs_autograd():
     d = lambda t: t.detach().to(DEV).contiguous()
     sc = torch.zeros(8, device=DEV)
     glp, ge, gv = (torch.empty(B, device=DEV) for _ in range(3))
-    rc = _lib.lib().gnbv_ppo_loss(d(lp).data_ptr(), d(ent).data_ptr(), d(v).data_ptr(), d(old_v).data_ptr(), d(old_lp).data_ptr(),
-                                  d(adv).data_ptr(), d(ret).data_ptr(), B, 0.2, 0.2, 0.01, 0.8, 10.0, 1, sc.data_ptr(),
+    args = [d(x) for x in (lp, ent, v, old_v, old_lp, adv, ret)]       # keep the device copies alive across the launch
+    rc = _lib.lib().gnbv_ppo_loss(*[a.data_ptr() for a in args], B, 0.2, 0.2, 0.01, 0.8, 10.0, 1, sc.data_ptr(),
                                   glp.data_ptr(), ge.data_ptr(), gv.data_ptr(), ops._stream())
     _lib.check(rc, "gnbv_ppo_loss")
     sc = sc.cpu()
     for i, k in enumerate(["policy_loss", "value_loss", "entropy_loss", "approx_kl", "clip_fraction"]):
-        assert abs(float(sc[i + 1]) - float(parts[k])) <= 1e-5 * max(1.0, abs(float(parts[k]))), k
-    assert abs(float(sc[0]) - float(loss)) <= 1e-5 * abs(float(loss))
+        assert abs(float(sc[i + 1]) - float(parts[k].detach())) <= 1e-5 * max(1.0, abs(float(parts[k].detach()))), k
+    assert abs(float(sc[0]) - float(loss.detach())) <= 1e-5 * abs(float(loss.detach()))
     assert rel_err(glp.cpu(), lp.grad) < 1e-5 and rel_err(ge.cpu(), ent.grad) < 1e-6 and rel_err(gv.cpu(), v.grad) < 1e-5
 
 
@@ -195,5 +216,6 @@ def test_clip_and_adam_match_torch():
         _lib.check(L.gnbv_grad_norm(gd.data_ptr(), n, 1.0, ws.data_ptr(), ops._stream()), "gnbv_grad_norm")
         _lib.check(L.gnbv_adam_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, ws.data_ptr(), 1e-4, 0.9, 0.999,
                                     1e-5, step, 1.0, ops._stream()), "gnbv_adam_step")
-        assert abs(float(ws[0]) / float(norm) - 1) < 1e-5
-        assert rel_err((p.cpu() - p0), (p_ref.detach() - p0)) < 1e-4
+        assert abs(float(ws[0]) / float(norm) - 1) < 1e-4      # torch sums 1.1 M squares in fp32; the kernel in double
+        # parameters are O(1) and the update O(1e-4): compare at fp32 resolution of the parameters (<= 2 ulp of 4.0)
+        assert float((p.cpu() - p_ref.detach()).abs().max()) <= 1e-6
