@@ -126,6 +126,8 @@ def test_fused_train_matches_torch_rerun(target_kl):
         if k.endswith("num_batches_tracked"):
             assert int(a) == int(b), k
             continue
+        if k.endswith("naive_encoder_grid.0.bias") or k.endswith("naive_encoder_grid.3.bias"):
+            continue          # zero-gradient parameters (conv bias under batch-stat BN): Adam amplifies rounding noise
         # parameters moved by ~lr per step: compare the displacement, not the O(1) values
         disp = (b - before[k].cpu().double()).abs().max()
         assert float((a - b).abs().max()) <= 0.02 * float(disp) + 1e-7, (k, float((a - b).abs().max()), float(disp))
