@@ -387,71 +387,90 @@ bn2_bwd_apply_kernel(const float* __restrict__ dact2, const float* __restrict__ 
     for (int q = 0; q < 4; ++q) o[q] = make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
 }
 
-// conv2 weight gradient.  Block = 4 position streams x 64 threads; thread (ci, cg) owns dW2[co = 4cg..4cg+3][ci][27 taps]
-// (108 accumulators).  dW2[co,ci,tap] = sum_{b,pos} dy2[b,pos,co] * relu(bn1(y1))[b, 2pos+tap, ci].
+// conv2 weight gradient.  dW2[co,ci,tap] = sum_{b,pos} dy2[b,pos,co] * relu(bn1(y1))[b, 2pos+tap, ci].
+// Block = 4 position streams x 64 threads; thread (ci, tg) owns all 16 co for input channel ci and the 7 taps
+// [7tg, 7tg+7) (112 accumulators): per position 4 LDG.128 (dy2, broadcast) + 7 LDG.32 feed 112 FMA.
 // Partials: part[blk][6912 + 16] in weight layout [co][ci][tap] followed by db2[16].
 constexpr int WG2_THREADS = 256;
-constexpr int WG2_POS_PER_STREAM = 32;
+constexpr int WG2_TT = 7;
+constexpr int WG2_MAX_BLOCKS = 592;
 constexpr int WG2_REC = C1 * C1 * TAPS + C1;
 __global__ void __launch_bounds__(WG2_THREADS)
 conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
-                   float* __restrict__ part, int G1, int G2, int64_t total_pos) {
+                   float* __restrict__ part, int G1, int G2, int64_t total_pos, int pos_per_stream) {
     extern __shared__ float sred[];           // [3][WG2_REC] for the cross-stream reduction
-    const int tid = threadIdx.x, stream = tid >> 6, t64 = tid & 63, ci = t64 >> 2, cg = t64 & 3;
+    const int tid = threadIdx.x, stream = tid >> 6, t64 = tid & 63, ci = t64 >> 2, tg = t64 & 3;
     const float a1 = stat1[2 * C1 + ci], b1 = stat1[3 * C1 + ci];
     const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
-    float acc[TAPS][4];
+    int off[WG2_TT];
 #pragma unroll
-    for (int t = 0; t < TAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-    float4 dbs = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t pos0 = ((int64_t)blockIdx.x * 4 + stream) * WG2_POS_PER_STREAM;
-    for (int k = 0; k < WG2_POS_PER_STREAM; ++k) {
-        const int64_t gp = pos0 + k;
-        if (gp >= total_pos) break;
+    for (int tt = 0; tt < WG2_TT; ++tt) {
+        const int tap = min(WG2_TT * tg + tt, TAPS - 1);
+        off[tt] = (((tap / 9) * G1 + (tap / 3) % 3) * G1 + tap % 3) * C1;
+    }
+    const int ntap = min(WG2_TT, TAPS - WG2_TT * tg);
+    float acc[WG2_TT][C1];
+#pragma unroll
+    for (int tt = 0; tt < WG2_TT; ++tt)
+#pragma unroll
+        for (int c = 0; c < C1; ++c) acc[tt][c] = 0.f;
+    float dbs[C1];
+#pragma unroll
+    for (int c = 0; c < C1; ++c) dbs[c] = 0.f;
+    const int64_t pos0 = ((int64_t)blockIdx.x * 4 + stream) * pos_per_stream;
+    const int64_t pos1 = min(total_pos, pos0 + pos_per_stream);
+    for (int64_t gp = pos0; gp < pos1; ++gp) {
         const int b = (int)(gp / P2), p = (int)(gp - (int64_t)b * P2);
         const int z2 = p % G2, t = p / G2, yy2 = t % G2, x2 = t / G2;
-        const float4 dy = __ldg(reinterpret_cast<const float4*>(dy2cl + gp * C1) + cg);
-        if (ci == 0) { dbs.x += dy.x; dbs.y += dy.y; dbs.z += dy.z; dbs.w += dy.w; }
+        const float4* dyp = reinterpret_cast<const float4*>(dy2cl + gp * C1);
+        const float4 d0 = __ldg(dyp), d1 = __ldg(dyp + 1), d2 = __ldg(dyp + 2), d3 = __ldg(dyp + 3);
+        const float dy[C1] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
+        if (t64 == 0) {
+#pragma unroll
+            for (int c = 0; c < C1; ++c) dbs[c] += dy[c];
+        }
         const float* in = y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2) * G1 + 2 * yy2) * G1 + 2 * z2) * C1 + ci;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int tt = 0; tt < WG2_TT; ++tt) {
+            if (tt < ntap) {
+                float x = __ldg(in + off[tt]);
+                x = fmaxf(fmaf(a1, x, b1), 0.f);
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    float x = __ldg(in + (((int64_t)i * G1 + j) * G1 + l) * C1);
-                    x = fmaxf(fmaf(a1, x, b1), 0.f);
-                    const int tap = (i * 3 + j) * 3 + l;
-                    acc[tap][0] = fmaf(dy.x, x, acc[tap][0]); acc[tap][1] = fmaf(dy.y, x, acc[tap][1]);
-                    acc[tap][2] = fmaf(dy.z, x, acc[tap][2]); acc[tap][3] = fmaf(dy.w, x, acc[tap][3]);
-                }
+                for (int c = 0; c < C1; ++c) acc[tt][c] = fmaf(dy[c], x, acc[tt][c]);
+            }
+        }
     }
     // cross-stream reduction in a fixed order: streams 1..3 publish, stream 0 adds them in order and writes the record
     if (stream > 0) {
         float* dst = sred + (stream - 1) * WG2_REC;
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t)
+        for (int tt = 0; tt < WG2_TT; ++tt)
+            if (tt < ntap) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dst[((4 * cg + q) * C1 + ci) * TAPS + t] = acc[t][q];
-        if (ci == 0) { dst[C1 * C1 * TAPS + 4 * cg + 0] = dbs.x; dst[C1 * C1 * TAPS + 4 * cg + 1] = dbs.y;
-                       dst[C1 * C1 * TAPS + 4 * cg + 2] = dbs.z; dst[C1 * C1 * TAPS + 4 * cg + 3] = dbs.w; }
+                for (int c = 0; c < C1; ++c) dst[(c * C1 + ci) * TAPS + WG2_TT * tg + tt] = acc[tt][c];
+            }
+        if (t64 == 0) {
+#pragma unroll
+            for (int c = 0; c < C1; ++c) dst[C1 * C1 * TAPS + c] = dbs[c];
+        }
     }
     __syncthreads();
     if (stream == 0) {
         float* out = part + (int64_t)blockIdx.x * WG2_REC;
 #pragma unroll
-        for (int t = 0; t < TAPS; ++t)
+        for (int tt = 0; tt < WG2_TT; ++tt)
+            if (tt < ntap) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int o = ((4 * cg + q) * C1 + ci) * TAPS + t;
-                out[o] = ((acc[t][q] + sred[o]) + sred[WG2_REC + o]) + sred[2 * WG2_REC + o];
+                for (int c = 0; c < C1; ++c) {
+                    const int o = (c * C1 + ci) * TAPS + WG2_TT * tg + tt;
+                    out[o] = ((acc[tt][c] + sred[o]) + sred[WG2_REC + o]) + sred[2 * WG2_REC + o];
+                }
             }
-        if (ci == 0) {
-            const float d4[4] = {dbs.x, dbs.y, dbs.z, dbs.w};
+        if (t64 == 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int o = C1 * C1 * TAPS + 4 * cg + q;
-                out[o] = ((d4[q] + sred[o]) + sred[WG2_REC + o]) + sred[2 * WG2_REC + o];
+            for (int c = 0; c < C1; ++c) {
+                const int o = C1 * C1 * TAPS + c;
+                out[o] = ((dbs[c] + sred[o]) + sred[WG2_REC + o]) + sred[2 * WG2_REC + o];
             }
         }
     }
@@ -469,10 +488,13 @@ reduce_records_kernel(const float* __restrict__ part, int nrec, int rec, float* 
     else out_b[j - na] = (float)s;
 }
 
-// conv2 data gradient + ReLU/BN1 backward statistics.  One thread per conv1-output voxel, 16 input channels.
+// conv2 data gradient + ReLU/BN1 backward statistics.
 //   dact1[b,vi,ci] = sum_{taps with (vi - tap) even and in range} sum_co dy2[b,(vi-tap)/2,co] * W2[co,ci,tap]
 //   g1 = dact1 * [bn1(y1) > 0]  -> stored channels-last; per-block (sum g1, sum g1*xhat1) partials -> bpart[blk][32]
+// One thread owns 4 conv1-output voxels of equal z parity (z = zpar + 2(4zq + s)) x 16 input channels: the 4 voxels
+// share their tap set, so each LDS.128 of weights feeds 16 FMA.
 constexpr int DG2_THREADS = 128;
+constexpr int DG2_ZT = 4;
 __global__ void __launch_bounds__(DG2_THREADS)
 conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w, const float* __restrict__ y1,
                    const float* __restrict__ stat1, float* __restrict__ g1, float* __restrict__ bpart, int G1, int G2) {
@@ -485,67 +507,89 @@ conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w,
     }
     __syncthreads();
     const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
-    const int p = blockIdx.x * DG2_THREADS + tid;
-    const bool valid = p < P1;
-    float acc[C1];
+    const int ZQ = ((G1 + 1) / 2 + DG2_ZT - 1) / DG2_ZT;
+    const int items = G1 * G1 * 2 * ZQ;
+    const int item = blockIdx.x * DG2_THREADS + tid;
+    const bool active = item < items;
+    float acc[DG2_ZT][C1];
 #pragma unroll
-    for (int c = 0; c < C1; ++c) acc[c] = 0.f;
+    for (int s = 0; s < DG2_ZT; ++s)
+#pragma unroll
+        for (int c = 0; c < C1; ++c) acc[s][c] = 0.f;
     float s1[C1], s2[C1];
-    if (valid) {
-        const int zi = p % G1, t = p / G1, yi = t % G1, xi = t / G1;
+#pragma unroll
+    for (int c = 0; c < C1; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+    if (active) {
+        int t = item;
+        const int zq = t % ZQ; t /= ZQ;
+        const int zpar = t & 1; t >>= 1;
+        const int yi = t % G1, xi = t / G1;
+        const int zfirst = zpar + 2 * DG2_ZT * zq;                   // z of s = 0; z(s) = zfirst + 2s
         for (int i = 0; i < 3; ++i) {
             const int xr = xi - i;
             if (xr < 0 || (xr & 1) || (xr >> 1) >= G2) continue;
             for (int j = 0; j < 3; ++j) {
                 const int yr = yi - j;
                 if (yr < 0 || (yr & 1) || (yr >> 1) >= G2) continue;
+                const int64_t row2 = ((int64_t)b * P2 + ((int64_t)(xr >> 1) * G2 + (yr >> 1)) * G2) * C1;
                 for (int l = 0; l < 3; ++l) {
-                    const int zr = zi - l;
-                    if (zr < 0 || (zr & 1) || (zr >> 1) >= G2) continue;
+                    if ((zpar - l) & 1) continue;
+                    const int z2first = ((zpar - l) >> 1) + DG2_ZT * zq;   // arithmetic shift: (0-2)>>1 == -1
                     const int tap = (i * 3 + j) * 3 + l;
-                    const int64_t p2 = ((int64_t)(xr >> 1) * G2 + (yr >> 1)) * G2 + (zr >> 1);
-                    const float4* dyp = reinterpret_cast<const float4*>(dy2cl + ((int64_t)b * P2 + p2) * C1);
 #pragma unroll
                     for (int oq = 0; oq < 4; ++oq) {
-                        const float4 dv = __ldg(dyp + oq);
-                        const float d4[4] = {dv.x, dv.y, dv.z, dv.w};
+                        float4 dv[DG2_ZT];
+#pragma unroll
+                        for (int s = 0; s < DG2_ZT; ++s) {
+                            const int z2 = z2first + s;
+                            const bool ok = z2 >= 0 && z2 < G2 && (zfirst + 2 * s) < G1;
+                            dv[s] = ok ? __ldg(reinterpret_cast<const float4*>(dy2cl + row2 + (int64_t)z2 * C1) + oq)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
 #pragma unroll
                         for (int oo = 0; oo < 4; ++oo) {
                             const float4* wr = reinterpret_cast<const float4*>(ws[tap][4 * oq + oo]);
 #pragma unroll
                             for (int cq = 0; cq < 4; ++cq) {
                                 const float4 wv = wr[cq];
-                                acc[4 * cq + 0] = fmaf(d4[oo], wv.x, acc[4 * cq + 0]);
-                                acc[4 * cq + 1] = fmaf(d4[oo], wv.y, acc[4 * cq + 1]);
-                                acc[4 * cq + 2] = fmaf(d4[oo], wv.z, acc[4 * cq + 2]);
-                                acc[4 * cq + 3] = fmaf(d4[oo], wv.w, acc[4 * cq + 3]);
+#pragma unroll
+                                for (int s = 0; s < DG2_ZT; ++s) {
+                                    const float d = oo == 0 ? dv[s].x : (oo == 1 ? dv[s].y : (oo == 2 ? dv[s].z : dv[s].w));
+                                    acc[s][4 * cq + 0] = fmaf(d, wv.x, acc[s][4 * cq + 0]);
+                                    acc[s][4 * cq + 1] = fmaf(d, wv.y, acc[s][4 * cq + 1]);
+                                    acc[s][4 * cq + 2] = fmaf(d, wv.z, acc[s][4 * cq + 2]);
+                                    acc[s][4 * cq + 3] = fmaf(d, wv.w, acc[s][4 * cq + 3]);
+                                }
                             }
                         }
                     }
                 }
             }
         }
-        const float4* yp = reinterpret_cast<const float4*>(y1 + ((int64_t)b * P1 + p) * C1);
-        float4* gp = reinterpret_cast<float4*>(g1 + ((int64_t)b * P1 + p) * C1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 yv = __ldg(yp + q);
-            const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
-            float o4[4];
+        for (int s = 0; s < DG2_ZT; ++s) {
+            const int zi = zfirst + 2 * s;
+            if (zi >= G1) continue;
+            const int64_t p = ((int64_t)xi * G1 + yi) * G1 + zi;
+            const float4* yp = reinterpret_cast<const float4*>(y1 + ((int64_t)b * P1 + p) * C1);
+            float4* gp = reinterpret_cast<float4*>(g1 + ((int64_t)b * P1 + p) * C1);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int c = 4 * q + e;
-                const float pre = fmaf(stat1[2 * C1 + c], y4[e], stat1[3 * C1 + c]);
-                const float g = pre > 0.f ? acc[c] : 0.f;
-                o4[e] = g;
-                s1[c] = g;
-                s2[c] = g * ((y4[e] - stat1[c]) * stat1[C1 + c]);
+            for (int q = 0; q < 4; ++q) {
+                const float4 yv = __ldg(yp + q);
+                const float y4[4] = {yv.x, yv.y, yv.z, yv.w};
+                float o4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * q + e;
+                    const float pre = fmaf(stat1[2 * C1 + c], y4[e], stat1[3 * C1 + c]);
+                    const float g = pre > 0.f ? acc[s][c] : 0.f;
+                    o4[e] = g;
+                    s1[c] += g;
+                    s2[c] = fmaf(g, (y4[e] - stat1[c]) * stat1[C1 + c], s2[c]);
+                }
+                gp[q] = make_float4(o4[0], o4[1], o4[2], o4[3]);
             }
-            gp[q] = make_float4(o4[0], o4[1], o4[2], o4[3]);
         }
-    } else {
-#pragma unroll
-        for (int c = 0; c < C1; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     }
 #pragma unroll
     for (int c = 0; c < C1; ++c) {
@@ -563,22 +607,24 @@ conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w,
 
 // conv1 weight gradient with the BN1 backward applied on the fly:
 //   dy1 = a1 * (g1 - S1/n - xhat1 * S2/n);  dW1[co,tap] = sum dy1[b,p,co] * tri[b, 2p+tap];  db1[co] = sum dy1
-// Groups of 8 threads share a position: thread (cg, th) owns co = 4cg..4cg+3 and taps [14*th, min(27, 14*th+14)).
+// Groups of 4 threads share a stream of z-pairs (z1 = 2m, 2m+1); thread cg owns co = 4cg..4cg+3 x all 27 taps
+// (108 accumulators).  The two voxels of a pair read the same 5-float input rows (one LDG.128 + one LDG.32 per row when
+// the grid row is 16 B aligned): 216 FMA per 22 loads.
 constexpr int WG1_THREADS = 256;
-constexpr int WG1_POS_PER_STREAM = 64;
+constexpr int WG1_MAX_BLOCKS = 1184;
 constexpr int WG1_REC = C1 * TAPS + C1;
 __global__ void __launch_bounds__(WG1_THREADS)
 conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
-                   const float* __restrict__ g1,
-                   const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ coef,
-                   float* __restrict__ part, int G, int G1, int64_t total_pos) {
+                   const float* __restrict__ g1, const float* __restrict__ y1, const float* __restrict__ stat1,
+                   const float* __restrict__ coef, float* __restrict__ part, int G, int G1, int64_t total_items,
+                   int items_per_stream, int vec_ok) {
     __shared__ float red[WG1_THREADS / 32][WG1_REC];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int grp = tid >> 3, t8 = tid & 7, cg = t8 >> 1, th = t8 & 1;
-    const int P1 = G1 * G1 * G1;
-    float acc[14][4];
+    const int grp = tid >> 2, cg = tid & 3;
+    const int P1 = G1 * G1 * G1, M = (G1 + 1) / 2, items_per_sample = G1 * G1 * M;
+    float acc[TAPS][4];
 #pragma unroll
-    for (int t = 0; t < 14; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    for (int t = 0; t < TAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
     float dbs[4] = {0.f, 0.f, 0.f, 0.f};
     float a1[4], mean[4], invstd[4], k1[4], k2[4];
 #pragma unroll
@@ -586,63 +632,84 @@ conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, const int6
         const int c = 4 * cg + q;
         mean[q] = stat1[c]; invstd[q] = stat1[C1 + c]; a1[q] = stat1[2 * C1 + c]; k1[q] = coef[c]; k2[q] = coef[C1 + c];
     }
-    const int64_t pos0 = ((int64_t)blockIdx.x * (WG1_THREADS / 8) + grp) * WG1_POS_PER_STREAM;
-    for (int k = 0; k < WG1_POS_PER_STREAM; ++k) {
-        const int64_t gp = pos0 + k;
-        if (gp >= total_pos) break;
-        const int b = (int)(gp / P1), p = (int)(gp - (int64_t)b * P1);
-        const int z1 = p % G1, t = p / G1, yy = t % G1, xx = t / G1;
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(g1 + gp * C1) + cg);
-        const float4 yv = __ldg(reinterpret_cast<const float4*>(y1 + gp * C1) + cg);
-        const float g4[4] = {gv.x, gv.y, gv.z, gv.w}, y4[4] = {yv.x, yv.y, yv.z, yv.w};
-        float dy[4];
+    const int64_t it0 = ((int64_t)blockIdx.x * (WG1_THREADS / 4) + grp) * items_per_stream;
+    const int64_t it1 = min(total_items, it0 + items_per_stream);
+    for (int64_t it = it0; it < it1; ++it) {
+        const int b = (int)(it / items_per_sample);
+        int t = (int)(it - (int64_t)b * items_per_sample);
+        const int m = t % M; t /= M;
+        const int yy = t % G1, xx = t / G1;
+        const int z1 = 2 * m;
+        const bool two = z1 + 1 < G1;
+        const int64_t gp = (int64_t)b * P1 + ((int64_t)xx * G1 + yy) * G1 + z1;
+        float dy[2][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            dy[q] = a1[q] * (g4[q] - k1[q] - ((y4[q] - mean[q]) * invstd[q]) * k2[q]);
-            if (th == 0) dbs[q] += dy[q];
+        for (int v = 0; v < 2; ++v) {
+            if (v == 0 || two) {
+                const float4 gv = __ldg(reinterpret_cast<const float4*>(g1 + (gp + v) * C1) + cg);
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(y1 + (gp + v) * C1) + cg);
+                const float g4[4] = {gv.x, gv.y, gv.z, gv.w}, y4[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    dy[v][q] = a1[q] * (g4[q] - k1[q] - ((y4[q] - mean[q]) * invstd[q]) * k2[q]);
+                    dbs[q] += dy[v][q];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dy[v][q] = 0.f;
+            }
         }
         const float* in = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off + ((int64_t)(2 * xx) * G + 2 * yy) * G + 2 * z1;
 #pragma unroll
-        for (int tt = 0; tt < 14; ++tt) {
-            const int tap = 14 * th + tt;
-            if (tap < TAPS) {
-                const int i = tap / 9, j = (tap / 3) % 3, l = tap % 3;
-                const float v = __ldg(in + ((int64_t)i * G + j) * G + l);
-                acc[tt][0] = fmaf(dy[0], v, acc[tt][0]); acc[tt][1] = fmaf(dy[1], v, acc[tt][1]);
-                acc[tt][2] = fmaf(dy[2], v, acc[tt][2]); acc[tt][3] = fmaf(dy[3], v, acc[tt][3]);
-            }
-        }
-    }
-    // reduce the 4 groups of a warp (lanes differing in bits 3,4), then the 8 warps in order
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int tt = 0; tt < 14; ++tt)
+            for (int j = 0; j < 3; ++j) {
+                const float* r = in + ((int64_t)i * G + j) * G;
+                float x[5];
+                if (vec_ok) {
+                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(r));
+                    x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+                } else {
+                    x[0] = __ldg(r); x[1] = __ldg(r + 1); x[2] = __ldg(r + 2); x[3] = two ? __ldg(r + 3) : 0.f;
+                }
+                x[4] = two ? __ldg(r + 4) : 0.f;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const int tap = (i * 3 + j) * 3 + l;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        acc[tap][q] = fmaf(dy[0][q], x[l], acc[tap][q]);
+                        acc[tap][q] = fmaf(dy[1][q], x[l + 2], acc[tap][q]);
+                    }
+                }
+            }
+    }
+    // reduce the 8 streams of a warp (lanes differing in bits 2,3,4), then the 8 warps in a fixed order
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            float v = acc[tt][q];
+            float v = acc[t][q];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
             v += __shfl_xor_sync(0xffffffffu, v, 8);
             v += __shfl_xor_sync(0xffffffffu, v, 16);
-            acc[tt][q] = v;
+            acc[t][q] = v;
         }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         float v = dbs[q];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         dbs[q] = v;
     }
-    if (lane < 8) {
+    if (lane < 4) {
 #pragma unroll
-        for (int tt = 0; tt < 14; ++tt) {
-            const int tap = 14 * th + tt;
-            if (tap < TAPS) {
+        for (int t = 0; t < TAPS; ++t)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) red[wid][(4 * cg + q) * TAPS + tap] = acc[tt][q];
-            }
-        }
-        if (th == 0) {
+            for (int q = 0; q < 4; ++q) red[wid][(4 * cg + q) * TAPS + t] = acc[t][q];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) red[wid][C1 * TAPS + 4 * cg + q] = dbs[q];
-        }
+        for (int q = 0; q < 4; ++q) red[wid][C1 * TAPS + 4 * cg + q] = dbs[q];
     }
     __syncthreads();
     for (int j = tid; j < WG1_REC; j += WG1_THREADS) {
@@ -651,6 +718,46 @@ conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, const int6
         for (int w = 0; w < WG1_THREADS / 32; ++w) t += red[w][j];
         part[(int64_t)blockIdx.x * WG1_REC + j] = t;
     }
+}
+
+// ---- two-level reductions of the per-block statistics (keeps the final single-block kernels short) -----------------
+constexpr int MERGE_FAN = 64;
+// forward BN partials (mean, M2, count) -> one record per MERGE_FAN input records (same layout)
+__global__ void __launch_bounds__(32 * C1)
+bn_merge_kernel(const float* __restrict__ part, int nblk, float* __restrict__ out) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * MERGE_FAN, k1 = min(nblk, k0 + MERGE_FAN);
+    double n = 0, mean = 0, M2 = 0;
+    for (int k = k0 + lane; k < k1; k += 32) {
+        const float* pr = part + (int64_t)k * PART_STRIDE;
+        chan_merge(n, mean, M2, (double)pr[2 * C1], (double)pr[c], (double)pr[C1 + c]);
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+               M2b = __shfl_xor_sync(0xffffffffu, M2, o);
+        double n_lo = (lane & o) ? nb : n, m_lo = (lane & o) ? mb : mean, q_lo = (lane & o) ? M2b : M2;
+        double n_hi = (lane & o) ? n : nb, m_hi = (lane & o) ? mean : mb, q_hi = (lane & o) ? M2 : M2b;
+        chan_merge(n_lo, m_lo, q_lo, n_hi, m_hi, q_hi);
+        n = n_lo; mean = m_lo; M2 = q_lo;
+    }
+    if (lane == 0) {
+        float* o = out + (int64_t)blockIdx.x * PART_STRIDE;
+        o[c] = (float)mean; o[C1 + c] = (float)M2;
+        if (c == 0) o[2 * C1] = (float)n;
+    }
+}
+
+// backward BN partial sums, layout B (S1[16], S2[16]) -> one record per MERGE_FAN input records
+__global__ void __launch_bounds__(32 * C1)
+sum_merge_kernel(const float* __restrict__ rec, int nrec, float* __restrict__ out) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = blockIdx.x * MERGE_FAN, k1 = min(nrec, k0 + MERGE_FAN);
+    double s1 = 0, s2 = 0;
+    for (int k = k0 + lane; k < k1; k += 32) { s1 += rec[(int64_t)k * 2 * C1 + c]; s2 += rec[(int64_t)k * 2 * C1 + C1 + c]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) { out[(int64_t)blockIdx.x * 2 * C1 + c] = (float)s1; out[(int64_t)blockIdx.x * 2 * C1 + C1 + c] = (float)s2; }
 }
 
 }  // namespace gnbv
@@ -687,7 +794,9 @@ struct EncWs {
     size_t pe, h1, cat, y1, part1, stat1, y2, part2, stat2, act2, gemm, total;
     // backward-only
     size_t dz, dcat, dh1, dact2, dy2cl, g1, bn2part, coef2, bpart1, coef1, wg2part, wg1part;
-    int nblk_dg, nblk_wg2, nblk_wg1;
+    int nblk_dg, nblk_wg2, nblk_wg1, wg2_pps, wg1_ips;
+    int64_t wg1_items;
+    size_t merge1, merge2, bmerge1;
 };
 
 EncWs make_ws(const EncDims& d, bool backward) {
@@ -704,16 +813,22 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.y2 = take(B * (size_t)d.flat2);
     w.part2 = take(B * (size_t)d.nblk2 * PART_STRIDE);
     w.stat2 = take(4 * C1);
+    w.merge1 = take((size_t)ceil_div(B * (size_t)d.nblk1, MERGE_FAN) * PART_STRIDE);
+    w.merge2 = take((size_t)ceil_div(B * (size_t)d.nblk2, MERGE_FAN) * PART_STRIDE);
     w.act2 = take(B * (size_t)d.flat2);
     size_t g = 0;
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, 4 * d.S));
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, d.HID));
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, (int)d.flat2));
     g = std::max(g, gemm_workspace_floats(d.B, d.FEAT, 2 * d.HID));
+    w.bmerge1 = 0;
     w.dz = w.dcat = w.dh1 = w.dact2 = w.dy2cl = w.g1 = w.bn2part = w.coef2 = w.bpart1 = w.coef1 = w.wg2part = w.wg1part = 0;
-    w.nblk_dg = (int)ceil_div(d.P1, DG2_THREADS);
-    w.nblk_wg2 = (int)ceil_div((int64_t)d.B * d.P2, 4 * WG2_POS_PER_STREAM);
-    w.nblk_wg1 = (int)ceil_div((int64_t)d.B * d.P1, (WG1_THREADS / 8) * WG1_POS_PER_STREAM);
+    w.nblk_dg = (int)ceil_div((int64_t)d.G1 * d.G1 * 2 * ceil_div((d.G1 + 1) / 2, DG2_ZT), DG2_THREADS);
+    w.wg2_pps = (int)std::max<int64_t>(16, ceil_div((int64_t)d.B * d.P2, (int64_t)WG2_MAX_BLOCKS * 4));
+    w.nblk_wg2 = (int)ceil_div((int64_t)d.B * d.P2, 4 * (int64_t)w.wg2_pps);
+    w.wg1_items = (int64_t)d.B * d.G1 * d.G1 * ((d.G1 + 1) / 2);
+    w.wg1_ips = (int)std::max<int64_t>(16, ceil_div(w.wg1_items, (int64_t)WG1_MAX_BLOCKS * (WG1_THREADS / 4)));
+    w.nblk_wg1 = (int)ceil_div(w.wg1_items, (int64_t)(WG1_THREADS / 4) * w.wg1_ips);
     if (backward) {
         w.dz = take(B * d.FEAT);
         w.dcat = take(B * 2 * d.HID);
@@ -725,6 +840,7 @@ EncWs make_ws(const EncDims& d, bool backward) {
         w.coef2 = take(2 * C1);
         w.bpart1 = take(B * (size_t)w.nblk_dg * 2 * C1);
         w.coef1 = take(2 * C1);
+        w.bmerge1 = take((size_t)ceil_div(B * (size_t)w.nblk_dg, MERGE_FAN) * 2 * C1);
         w.wg2part = take((size_t)w.nblk_wg2 * WG2_REC);
         w.wg1part = take((size_t)w.nblk_wg1 * WG1_REC);
         g = std::max(g, gemm_workspace_floats(d.B, 2 * d.HID, d.FEAT));
@@ -787,9 +903,12 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
                                                                       ws + w.y1, part1, d.G, d.G1);
     GNBV_LAUNCH_CHECK("conv1_fwd_kernel");
-    if (training)
-        bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(part1, B * d.nblk1, p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, p->bn1_nbt,
+    if (training) {
+        const int nm = (int)ceil_div((int64_t)B * d.nblk1, MERGE_FAN);
+        bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part1, B * d.nblk1, ws + w.merge1);
+        bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.merge1, nm, p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, p->bn1_nbt,
                                                       ws + w.stat1, 1e-5f, 0.1f);
+    }
     else
         bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, ws + w.stat1, 1e-5f);
     GNBV_LAUNCH_CHECK("bn1 statistics");
@@ -797,9 +916,12 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     conv2_fwd_kernel<<<dim3(d.nblk2, B), CONV2_THREADS, 0, stream>>>(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2,
                                                                       part2, d.G1, d.G2);
     GNBV_LAUNCH_CHECK("conv2_fwd_kernel");
-    if (training)
-        bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(part2, B * d.nblk2, p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, p->bn2_nbt,
+    if (training) {
+        const int nm = (int)ceil_div((int64_t)B * d.nblk2, MERGE_FAN);
+        bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part2, B * d.nblk2, ws + w.merge2);
+        bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.merge2, nm, p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, p->bn2_nbt,
                                                       ws + w.stat2, 1e-5f, 0.1f);
+    }
     else
         bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, ws + w.stat2, 1e-5f);
     GNBV_LAUNCH_CHECK("bn2 statistics");
@@ -875,18 +997,23 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     const size_t smem_wg2 = 3 * (size_t)WG2_REC * 4;
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
     conv2_wgrad_kernel<<<w.nblk_wg2, WG2_THREADS, smem_wg2, stream>>>(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, d.G1,
-                                                                       d.G2, (int64_t)B * d.P2);
+                                                                       d.G2, (int64_t)B * d.P2, w.wg2_pps);
     GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);
     conv2_dgrad_kernel<<<dim3(w.nblk_dg, B), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1,
                                                                         ws + w.bpart1, d.G1, d.G2);
     GNBV_LAUNCH_CHECK("conv2_dgrad_kernel");
-    bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bpart1, B * w.nblk_dg, 2 * C1, 1, (double)B * d.P1, gr->bn1_w, gr->bn1_b,
-                                                      ws + w.coef1, training ? 0 : 1);
+    {
+        const int nm = (int)ceil_div((int64_t)B * w.nblk_dg, MERGE_FAN);
+        sum_merge_kernel<<<nm, 32 * C1, 0, stream>>>(ws + w.bpart1, B * w.nblk_dg, ws + w.bmerge1);
+        bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bmerge1, nm, 2 * C1, 1, (double)B * d.P1, gr->bn1_w, gr->bn1_b,
+                                                          ws + w.coef1, training ? 0 : 1);
+    }
     // ---- conv1 backward (weights only: the input is data)
+    const int vec1 = (d.G % 4 == 0) && (obs_row_stride % 4 == 0) && (state_dim % 4 == 0) && (((uintptr_t)obs & 15) == 0);
     conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
-                                                                ws + w.coef1, ws + w.wg1part, d.G, d.G1, (int64_t)B * d.P1);
+                                                                ws + w.coef1, ws + w.wg1part, d.G, d.G1, w.wg1_items, w.wg1_ips, vec1);
     GNBV_LAUNCH_CHECK("conv1_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, w.nblk_wg1, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
     GNBV_LAUNCH_CHECK("reduce_records_kernel");
