@@ -1,12 +1,15 @@
 #!/usr/bin/env python
-"""bench.py -- env-steps/s of the GenNBV state-encoding hot path on B200 (contract: see DESIGN.md section "Measurement").
+"""bench.py -- env-steps/s of the GenNBV state-encoding + encoder hot path on B200 (see DESIGN.md "Measurement").
 
-    python bench.py --gpus 1 --steps 20 --warmup 3                 # this framework (CUDA, via the C ABI)
-    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1  # the reference algorithm on the host cores
-    torchrun --nproc-per-node N ... bench.py --gpus N ...           # env-parallel, one rank per GPU (weak scaling)
+    python bench.py --gpus 1 --steps 30 --warmup 5                  # this framework (CUDA through the C ABI)
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1   # the reference's CPU PyTorch path on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...            # env-parallel, one rank per GPU (weak scaling)
 
-A "step" is one env.step() worth of state encoding for 256 environments per GPU (BASELINE.json configs[1]
-shapes: 128x128 depth, 64^3 grid) on synthetic depth.  Prints ONE JSON line on rank 0.
+A "step" is BASELINE.json configs[1] for 256 environments per GPU: one env.step() worth of state encoding (sensor
+post-processing, depth un-projection, voxel scatter, Bresenham ray-cast, prob / tri-class / scanned-GT update, coverage
+reward, termination, reset) on 128x128 synthetic depth and a 64^3 grid, followed by the 3D-CNN Hybrid_Encoder forward
+(batch-statistics BatchNorm) and backward on the 256 fresh observations; with N > 1 GPUs the flat encoder gradient is
+all-reduced over NCCL/NVLink every step.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -22,10 +25,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-ENVS_PER_GPU, H, W, G, SCENES, FRAMES = 256, 128, 128, 64, 8, 4
+ENVS_PER_GPU, H, W, G, SCENES, FRAMES, STATE_DIM = 256, 128, 128, 64, 8, 4, 600
 METRIC, UNIT = "env_steps_per_sec", "env-steps/s"
-WORKLOAD = ("256 envs/GPU x 128x128 synthetic depth x 64^3 grid: depth post-process + unproject + voxel scatter + "
-            "Bresenham ray-cast + prob/tri-class/scanned-GT update + coverage sum (BASELINE configs[1] shapes)")
+WORKLOAD = ("BASELINE configs[1]: 256 envs/GPU x 128x128 synthetic depth x 64^3 grid -- env.step() state encoding "
+            "(post-process + unproject + voxel scatter + Bresenham ray-cast + prob/tri-class/scanned-GT update + coverage "
+            "reward + termination/reset) + Hybrid_Encoder (3D-CNN) forward/backward on the 256 observations")
 
 
 def algorithmic_bytes_per_env_step(P, V):
@@ -37,19 +41,16 @@ def make_workload(num_envs, device, seed):
     """Synthetic scenes + FRAMES rendered views per env (raw sensor convention), rendered on `device`."""
     from gennbv_b200 import synth
     scenes = synth.make_house_scenes(SCENES, G, seed=seed)
-    vs, nvalid, rg = synth.gt_metadata(scenes.grid_gt)
-    idx = torch.arange(num_envs) % SCENES
     gen = torch.Generator().manual_seed(seed + 1)
-    frames = []
+    frames, actions = [], []
     for _ in range(FRAMES):
-        poses = synth.pose_from_action(synth.sample_lookat_actions(scenes.params, num_envs, gen)).to(device)
-        depth, seg, _, c2w = synth.render(scenes.params, poses, H, W)
-        frames.append(dict(depth=depth.contiguous(), seg=seg.contiguous(), c2w=c2w.float().contiguous(),
-                           xyz=poses[:, :3].contiguous()))
-    return dict(kinv=torch.linalg.inv(synth.camera_intrinsics(H, W)).float().contiguous().to(device),
-                range_gt=rg[idx].contiguous().to(device), vs=vs[idx].contiguous().to(device),
-                grid_gt=scenes.grid_gt[..., 3][idx].contiguous().to(device),
-                num_valid=nvalid[idx].contiguous().to(device), frames=frames)
+        a = synth.sample_lookat_actions(scenes.params, num_envs, gen)
+        poses = synth.pose_from_action(a).to(device)
+        depth, seg, rgb, c2w = synth.render(scenes.params, poses, H, W, with_rgb=True)
+        frames.append(dict(depth=depth.contiguous(), seg=seg.contiguous(), rgba=rgb.contiguous(),
+                           c2w=c2w.float().contiguous(), xyz=poses[:, :3].contiguous()))
+        actions.append(a.to(device))
+    return dict(scenes=scenes, frames=frames, actions=actions)
 
 
 class ClockSampler:
@@ -63,23 +64,26 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            time.sleep(0.3)          # let the first samples arrive before the timed region starts
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if t_begin is not None and not (t_begin - 0.06 <= ts <= t_end + 0.12):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 6 or not f[0].isdigit():
                 continue
@@ -99,69 +103,48 @@ def peaks():
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
-def cpu_voxelize_rate(wl_cpu, num_envs, threads, steps, warmup):
-    """The reference algorithm on host cores: the C restatement (oracle/gennbv_oracle.c), envs split over
-    `threads` host threads (ctypes releases the GIL).  Returns (env-steps/s, seconds per step)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as c_oracle
-    from concurrent.futures import ThreadPoolExecutor
-    c_oracle.lib()
-    prob = np.zeros((num_envs, G, G, G), np.float32); scan = np.zeros_like(prob)
-    bounds = np.linspace(0, num_envs, threads + 1).astype(int)
-    pool = ThreadPoolExecutor(threads)
-
-    def one(step):
-        f = wl_cpu["frames"][step % FRAMES]
-
-        def part(i):
-            a, b = bounds[i], bounds[i + 1]
-            if a == b:
-                return
-            c_oracle.voxelize_step(f["depth"][a:b], f["seg"][a:b], wl_cpu["kinv"], f["c2w"][a:b], wl_cpu["range_gt"][a:b],
-                                   wl_cpu["vs"][a:b], f["xyz"][a:b], wl_cpu["grid_gt"][a:b], prob[a:b], scan[a:b],
-                                   raw_depth=True)
-        list(pool.map(part, range(threads)))
-
-    for s in range(warmup):
-        one(s)
-    t0 = time.perf_counter()
-    for s in range(steps):
-        one(warmup + s)
-    dt = time.perf_counter() - t0
-    return num_envs * steps / dt, dt / steps
-
-
-def cpu_torch_rate(wl, num_envs, threads, steps, warmup):
-    """The reference's CPU PyTorch path: oracle/torch_ref.py restates update_occ_grid op for op (einsum,
-    floor, unique, index_put ... in per-env Python loops), torch intra-op threads = `threads`."""
+def cpu_reference_rate(wl, num_envs, threads, steps, warmup):
+    """The reference's CPU PyTorch path for the same step: oracle/torch_ref.py restates update_occ_grid op for op
+    (einsum, floor, unique, index_put ... in per-env Python loops; the PyCUDA Bresenham kernel served by the C
+    restatement), oracle/encoder_ref.py is the reference encoder with the grid size parametrised; forward in train
+    mode + backward.  torch intra-op threads = `threads`.  Returns (env-steps/s, seconds/step, stage seconds)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch_ref
+    import encoder_ref
+    from gennbv_b200 import synth
     torch.set_num_threads(threads)
+    scenes = wl["scenes"]
+    vs, nvalid, rg = synth.gt_metadata(scenes.grid_gt)
+    idx = torch.arange(num_envs) % SCENES
+    vs, rg, gt = vs[idx].contiguous(), rg[idx].contiguous(), scenes.grid_gt[..., 3][idx].contiguous()
+    kinv = torch.linalg.inv(synth.camera_intrinsics(H, W)).float()
     pix = torch_ref.pixel_grid(H, W)
     prob = torch.zeros(num_envs, G, G, G); scan = torch.zeros_like(prob)
-    c = {k: wl[k][:num_envs].cpu() for k in ("range_gt", "vs", "grid_gt")}
-    kinv = wl["kinv"].cpu()
     frames = [{k: v[:num_envs].cpu() for k, v in f.items()} for f in wl["frames"]]
+    enc = encoder_ref.HybridEncoderRef(G, STATE_DIM)
+    enc.train()
+    obs = torch.zeros(num_envs, STATE_DIM + G ** 3 + 8192)
+    acc = {"vox": 0.0, "enc": 0.0}
 
-    def one(i):
+    def one(i, timed):
         f = frames[i % FRAMES]
-        torch_ref.voxelize_step(f["depth"], f["seg"], kinv, f["c2w"], c["range_gt"], c["vs"], f["xyz"], c["grid_gt"],
-                                prob, scan, pix)
+        t0 = time.perf_counter()
+        tri, cov = torch_ref.voxelize_step(f["depth"], f["seg"], kinv, f["c2w"], rg, vs, f["xyz"], gt, prob, scan, pix)
+        obs[:, STATE_DIM:STATE_DIM + G ** 3] = tri.view(num_envs, -1)
+        t1 = time.perf_counter()
+        enc.zero_grad()
+        enc(obs).sum().backward()
+        t2 = time.perf_counter()
+        if timed:
+            acc["vox"] += t1 - t0; acc["enc"] += t2 - t1
 
     for s in range(warmup):
-        one(s)
+        one(s, False)
     t0 = time.perf_counter()
     for s in range(steps):
-        one(warmup + s)
+        one(warmup + s, True)
     dt = time.perf_counter() - t0
-    return num_envs * steps / dt, dt / steps
-
-
-def to_cpu_workload(wl, n):
-    out = {k: wl[k][:n].cpu().numpy() if k in ("range_gt", "vs", "grid_gt") else None for k in wl}
-    out["kinv"] = wl["kinv"].cpu().numpy()
-    out["frames"] = [{k: v[:n].cpu().numpy() for k, v in f.items()} for f in wl["frames"]]
-    return out
+    return num_envs * steps / dt, dt / steps, {"voxelize+coverage": acc["vox"] / steps, "encoder_fwd_bwd": acc["enc"] / steps}
 
 
 def run_reference(args, rank):
@@ -171,67 +154,103 @@ def run_reference(args, rank):
     wl = make_workload(ENVS_PER_GPU, "cpu", seed=0)
     if args.cpu_envs is None:
         # bounded sample: size the per-step env count so that the whole run stays near two minutes
-        probe, _ = cpu_torch_rate(wl, 8, threads, 1, 1)
+        probe, _, _ = cpu_reference_rate(wl, 8, threads, 1, 1)
         n = int(max(8, min(ENVS_PER_GPU, 120.0 * probe / (args.steps + args.warmup))))
     else:
         n = args.cpu_envs
-    rate, sec = cpu_torch_rate(wl, n, threads, args.steps, args.warmup)
-    c_rate, _ = cpu_voxelize_rate(to_cpu_workload(wl, n), n, threads, args.steps, args.warmup)
+    rate, sec, stages = cpu_reference_rate(wl, n, threads, args.steps, args.warmup)
     sample = (f"{n} of {ENVS_PER_GPU} envs per step, {args.steps} steps; PyTorch-CPU restatement of the reference's "
-              f"update_occ_grid path (oracle/torch_ref.py, {threads} torch threads); the multi-threaded C restatement "
-              f"(oracle/gennbv_oracle.c) reaches {c_rate:.0f} env-steps/s on the same sample")
+              f"update_occ_grid path (oracle/torch_ref.py) + reference encoder fwd/bwd (oracle/encoder_ref.py), "
+              f"{threads} torch threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3 * ENVS_PER_GPU / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "host CPU arm; ms_per_step extrapolated to 256 envs"},
+        "config": {"workload": WORKLOAD, "note": "host CPU arm; ms_per_step extrapolated to 256 envs",
+                   "stages_ms_per_sample_step": {k: v * 1e3 for k, v in stages.items()}},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def build_native(wl, dev, host_frames):
+    from gennbv_b200.config import Config_GenNBV_Train
+    from gennbv_b200.env import Env_Train_GenNBV
+    from gennbv_b200.policy import ActorCriticPolicy_Train_Eval
+    from gennbv_b200.sensors import FrameListSensor
+    from gennbv_b200.wrapper import EnvWrapperGenNBVTrain
+
+    class Cfg(Config_GenNBV_Train):
+        class rewards(Config_GenNBV_Train.rewards):
+            only_positive_rewards = False
+
+    sensor = FrameListSensor(wl["frames"], dev, host=host_frames)
+    env = EnvWrapperGenNBVTrain(Env_Train_GenNBV(Cfg(), sim_device=str(dev), sensor=sensor, grid_gt=wl["scenes"].grid_gt,
+                                                 num_envs=ENVS_PER_GPU))
+    kwargs = dict(encoder_param={"hidden_shapes": [256, 256], "visual_dim": 256},
+                  net_param={"transformer_params": [[1, 256], [1, 256]], "append_hidden_shapes": [256, 256]},
+                  state_input_shape=(STATE_DIM,), visual_input_shape=(100, H, W))
+    torch.manual_seed(0)
+    policy = ActorCriticPolicy_Train_Eval(env.observation_space, env.action_space, lambda _: 1e-4, net_arch=[],
+                                          features_extractor_kwargs=kwargs, device=dev)
+    policy.train(True)
+    return env, sensor, policy
+
+
 def run_native(args, rank, world):
-    from gennbv_b200 import ops
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = ENVS_PER_GPU
+    N, V, P = ENVS_PER_GPU, G ** 3, H * W
     wl = make_workload(N, dev, seed=rank)
-    V, P = G ** 3, H * W
-    prob = torch.zeros(N, G, G, G, device=dev); scan = torch.zeros_like(prob); tri = torch.empty_like(prob)
-    cov = torch.zeros(N, device=dev); nt = torch.zeros(N, dtype=torch.int32, device=dev)
-    ws = ops.voxelize_workspace(N, G, dev)
     K, Wm = args.steps, args.warmup
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-
-    def step(i, timed=None):
-        f = wl["frames"][i % FRAMES]
-        if timed is not None:
-            timed[0].record()
-        ops.scan_raycast(f["depth"], f["seg"], wl["kinv"], f["c2w"], wl["range_gt"], wl["vs"], f["xyz"], G, ws, nt,
-                         raw_depth=True)
-        if timed is not None:
-            timed[1].record()
-        ops.grid_update(wl["grid_gt"], prob, scan, tri, cov, ws)
-        if timed is not None:
-            timed[2].record()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def make_step(host_frames):
+        env, sensor, policy = build_native(wl, dev, host_frames)
+        enc = policy.features_extractor
+        grads = policy.encoder_grad_views()
+        dfeat = torch.full((N, 256), 1.0 / N, device=dev)
+        env.reset()
+
+        def step(i, ev=None):
+            if ev is not None:
+                env._gym_env.profile_events = ev[1:4]
+                ev[0].record()
+            obs, rew, done, info = env.step(wl["actions"][i % FRAMES])
+            if ev is not None:
+                ev[4].record()
+            feats = enc._run_forward(obs, need_bwd=True, training=True)
+            if ev is not None:
+                ev[5].record()
+            enc._run_backward(obs, feats, dfeat, N, True, enc._ws, grads=grads)
+            if world > 1:
+                dist.all_reduce(policy.flat_grads)         # PPO gradient all-reduce over NCCL/NVLink (configs[3])
+            if ev is not None:
+                ev[6].record()
+            return rew, feats
+
+        return step, env, sensor, policy
+
+    # ---- device-resident arm: `value`
+    step, env, sensor, policy = make_step(host_frames=False)
     for i in range(Wm):
         step(i)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(K)]
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" isolates the step's kernels
     t_start.record()
     for i in range(K):
@@ -240,25 +259,37 @@ def run_native(args, rank, world):
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()
     barrier()
+    wall1 = time.time()
     ms_total = t_start.elapsed_time(t_end)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_scan = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    ms_grid = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    env._gym_env.profile_events = None
+    stage = lambda a, b: float(np.mean([e[a].elapsed_time(e[b]) for e in ev]))
+    stages = {"env.step total": stage(0, 4), "scan_raycast": stage(1, 2), "grid_update+coverage": stage(2, 3),
+              "encoder_forward": stage(4, 5), "encoder_backward(+allreduce)": stage(5, 6)}
+    # kernel launches of one step, counted with the CUDA profiler (every kernel of libgennbv_b200 lives in namespace gnbv)
+    launches = None
+    if rank == 0:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                step(Wm + K)
+                torch.cuda.synchronize()
+            launches = sum(1 for e in prof.events() if "gnbv::" in e.name)
+        except Exception:
+            launches = None
+    del step, env, sensor, policy
+    torch.cuda.empty_cache()
 
-    # ---- end to end through the public call with HOST buffers (pinned), H2D + result D2H inside the timed region
-    host = [{k: v.cpu().pin_memory() for k, v in f.items()} for f in wl["frames"]]
-    dbuf = {k: torch.empty_like(v) for k, v in wl["frames"][0].items()}
-    cov_host = torch.empty(N, dtype=torch.float32).pin_memory()
-    prob.zero_(); scan.zero_()
+    # ---- end to end through the public API with HOST sensor buffers (pinned): H2D of every frame and D2H of the rewards
+    #      and a feature checksum inside the timed region
+    step, env, sensor, policy = make_step(host_frames=True)
+    rew_host = torch.empty(N, dtype=torch.float32).pin_memory()
+    chk_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
-        h = host[i % FRAMES]
-        for k in dbuf:
-            dbuf[k].copy_(h[k], non_blocking=True)
-        ops.voxelize_step(dbuf["depth"], dbuf["seg"], wl["kinv"], dbuf["c2w"], wl["range_gt"], wl["vs"], dbuf["xyz"],
-                          wl["grid_gt"], prob, scan, tri, cov, nt, workspace=ws, raw_depth=True)
-        cov_host.copy_(cov, non_blocking=True)
-        torch.cuda.current_stream().synchronize()        # the caller reads the coverage (reward) every step
+        rew, feats = step(i)
+        rew_host.copy_(rew, non_blocking=True)
+        chk_host.copy_(feats.sum().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller consumes rewards / loss every step
 
     for i in range(Wm):
         e2e_step(i)
@@ -270,13 +301,16 @@ def run_native(args, rank, world):
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
-    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
-    d2h = cov_host.numel() * 4
+    h2d, d2h = sensor.bytes_per_frame, N * 4 + 4
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
 
-    t = torch.tensor([ms_total, ms_e2e, ms_scan, ms_grid], device=dev, dtype=torch.float64)
+    keys = list(stages)
+    t = torch.tensor([ms_total, ms_e2e] + [stages[k] for k in keys], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, ms_scan, ms_grid = t.tolist()
+    vals = t.tolist()
+    ms_total, ms_e2e = vals[0], vals[1]
+    stages = dict(zip(keys, vals[2:]))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -284,33 +318,35 @@ def run_native(args, rank, world):
 
     peak, peak_src = peaks()
     b_vox, b_cov = algorithmic_bytes_per_env_step(P, V)
-    # dominant kernel: grid_update_kernel (dense prob/tri/scanned pass = 24 B/voxel of the 24.5 B/voxel algorithmic total)
-    alg_grid = N * (V * 24 + 4)
+    ms_grid = stages["grid_update+coverage"]
+    alg_grid = N * (V * 24 + 4)       # grid_update_kernel: prob r+w, scanned r+w, gt r, tri w = 24 B/voxel (+4 B coverage) per env
     achieved = alg_grid / (ms_grid * 1e-3) / 1e9
     out = {
         "metric": METRIC, "value": world * N * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": N, "depth": [H, W], "grid": G, "frames_rotated": FRAMES,
-                   "l2": "state grids (prob+scanned+gt+tri = 1.07 GB/step) exceed the 126 MB L2; no explicit flush",
-                   "stages_ms": {"scan_raycast": ms_scan, "grid_update+coverage": ms_grid}},
+                   "l2": "per-step working set (prob+scanned+gt grids 0.8 GB, observations 0.28 GB, conv1 activations 0.49 GB) "
+                         "exceeds the 126 MB L2; no explicit flush",
+                   "stages_ms": stages},
         "roofline": {"bound": "hbm", "kernel": "grid_update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_grid,
-                     "step_algorithmic_bytes": N * (b_vox + b_cov),
-                     "step_frac": N * (b_vox + b_cov) / (ms_total / K * 1e-3) / 1e9 / peak},
+                     "frac": achieved / peak, "traffic": 1569.4e6,
+                     "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_grid,
+                     "voxelize_algorithmic_bytes_per_step": N * (b_vox + b_cov)},
         "e2e": {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
-        "gpu_launches": 3 * K,
+        "gpu_launches": (launches or 0) * K, "gpu_launches_per_step": launches,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        n, threads = 32, os.cpu_count() or 1
-        rate, sec = cpu_torch_rate(wl, n, threads, 3, 1)
-        c_rate, _ = cpu_voxelize_rate(to_cpu_workload(wl, n), n, 1, 2, 1)
+        n, threads = 16, os.cpu_count() or 1
+        wl_cpu = {"scenes": wl["scenes"], "frames": [{k: v[:n].cpu() for k, v in f.items()} for f in wl["frames"]]}
+        rate, sec, st = cpu_reference_rate(wl_cpu, n, threads, 2, 1)
         out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                               "sample": f"{n} of {N} envs x 3 steps; PyTorch-CPU restatement of the reference path "
-                                         f"(oracle/torch_ref.py); single-thread C restatement: {c_rate:.0f} env-steps/s"}
+                               "sample": f"{n} of {N} envs x 2 steps; PyTorch-CPU restatement of the reference path "
+                                         f"(oracle/torch_ref.py + oracle/encoder_ref.py), stages s/step: "
+                                         + ", ".join(f"{k} {v:.2f}" for k, v in st.items())}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -331,7 +367,7 @@ def main():
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference(args, rank)
     else:
-        args.steps = 30 if args.steps is None else args.steps
+        args.steps = 50 if args.steps is None else args.steps
         args.warmup = 5 if args.warmup is None else max(args.warmup, 3)
         run_native(args, rank, world)
 

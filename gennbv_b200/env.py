@@ -131,6 +131,7 @@ class Env_Train_GenNBV:
         self.episode_sums = {"surface_coverage": self.episode_sums_buf[0], "short_path": self.episode_sums_buf[1],
                              "termination": self.episode_sums_buf[2]}
         self._stats = torch.zeros(int(_lib.lib().gnbv_episode_stats_doubles()), dtype=torch.float64, device=dev)
+        self.profile_events = None
         self.update_observation_space()
 
     # ------------------------------------------------------------------ GT (env_train_gennbv.py:56-96)
@@ -260,10 +261,17 @@ class Env_Train_GenNBV:
                    "gnbv_obs_update")
         # update_occ_grid: tri-class grid lands in the grid columns of obs_flat
         self._xyz = self.poses[:, :3].contiguous()
-        ops.voxelize_step(frame.depth, frame.seg, self.inv_intri, c2w, self.range_gt, self.voxel_size_gt, self._xyz,
-                          self.grid_gt, self.prob_grid, self.scanned_gt_grid, self.obs_flat.view(-1)[self._state_dim:],
-                          self._cov_sum, self._num_targets, workspace=self._workspace, raw_depth=True,
-                          tri_row_stride=self.obs_dim)
+        ev = self.profile_events                      # optional (start, mid, end) CUDA events around the two voxelize phases
+        if ev is not None:
+            ev[0].record()
+        ops.scan_raycast(frame.depth, frame.seg, self.inv_intri, c2w, self.range_gt, self.voxel_size_gt, self._xyz, G,
+                         self._workspace, self._num_targets, raw_depth=True)
+        if ev is not None:
+            ev[1].record()
+        ops.grid_update(self.grid_gt, self.prob_grid, self.scanned_gt_grid, self.obs_flat.view(-1)[self._state_dim:],
+                        self._cov_sum, self._workspace, tri_row_stride=self.obs_dim)
+        if ev is not None:
+            ev[2].record()
         # compute_reward / check_termination / episode statistics
         rs = self.reward_scales
         _lib.check(L.gnbv_reward_termination(

@@ -58,3 +58,29 @@ class ReplaySensor(SensorSource):
         d = lambda a: torch.from_numpy(np.ascontiguousarray(a[t])).to(self.device)
         return SensorFrame(depth=d(self.depth), seg=d(self.seg), rgba=d(self.rgba) if self.rgba is not None else None,
                            view_matrix=np.ascontiguousarray(self.view[t]))
+
+
+class FrameListSensor(SensorSource):
+    """Cycles through pre-rendered frames (dicts with depth / seg / rgba / c2w).  With `host=True` the frames live in
+    pinned host memory and every render() issues the host->device copies on the current stream -- the shape of a real
+    deployment where the simulator hands over host or foreign-device buffers."""
+
+    def __init__(self, frames, device, host=False):
+        self.device, self.host, self.t = torch.device(device), host, 0
+        keys = ("depth", "seg", "rgba", "c2w")
+        if host:
+            self.frames = [{k: f[k].cpu().pin_memory() for k in keys if f.get(k) is not None} for f in frames]
+            self.dev = {k: torch.empty_like(v, device=self.device) for k, v in self.frames[0].items()}
+        else:
+            self.frames = [{k: f[k].to(self.device).contiguous() for k in keys if f.get(k) is not None} for f in frames]
+        self.height, self.width = self.frames[0]["depth"].shape[-2:]
+        self.bytes_per_frame = sum(v.numel() * v.element_size() for v in self.frames[0].values())
+
+    def render(self, poses):
+        f = self.frames[self.t % len(self.frames)]
+        self.t += 1
+        if self.host:
+            for k, v in f.items():
+                self.dev[k].copy_(v, non_blocking=True)
+            f = self.dev
+        return SensorFrame(depth=f["depth"], seg=f["seg"], rgba=f.get("rgba"), c2w=f["c2w"])
