@@ -249,6 +249,8 @@ def run_native(args, rank, world):
     barrier()
     if rank == 0:
         sampler.start()
+    from gennbv_b200 import _lib
+    _lib.check(_lib.lib().gnbv_profile_enable(1), "gnbv_profile_enable")      # stage events inside the encoder calls
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
     torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" isolates the step's kernels
@@ -261,6 +263,8 @@ def run_native(args, rank, world):
     barrier()
     wall1 = time.time()
     ms_total = t_start.elapsed_time(t_end)
+    kernel_ms = {k: _lib.stage_ms(k) for k in _lib.ENCODER_STAGES}          # device time of each encoder stage, last timed step
+    _lib.lib().gnbv_profile_enable(0)
     env._gym_env.profile_events = None
     stage = lambda a, b: float(np.mean([e[a].elapsed_time(e[b]) for e in ev]))
     stages = {"env.step total": stage(0, 4), "scan_raycast": stage(1, 2), "grid_update+coverage": stage(2, 3),
@@ -321,6 +325,15 @@ def run_native(args, rank, world):
     ms_grid = stages["grid_update+coverage"]
     alg_grid = N * (V * 24 + 4)       # grid_update_kernel: prob r+w, scanned r+w, gt r, tri w = 24 B/voxel (+4 B coverage) per env
     achieved = alg_grid / (ms_grid * 1e-3) / 1e9
+    G1 = (G - 3) // 2 + 1
+    G2 = (G1 - 3) // 2 + 1
+    flops = {"fwd.conv1": 2 * N * G1 ** 3 * 16 * 27, "bwd.conv1_wgrad": 2 * N * G1 ** 3 * 16 * 27,
+             "fwd.conv2": 2 * N * G2 ** 3 * 16 * 432, "bwd.conv2_wgrad": 2 * N * G2 ** 3 * 16 * 432,
+             "bwd.conv2_dgrad": 2 * N * G2 ** 3 * 16 * 432, "fwd.grid_fc": 2 * N * 16 * G2 ** 3 * 256,
+             "bwd.grid_fc": 4 * N * 16 * G2 ** 3 * 256}
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12            # nominal fp32 FMA peak (no measured denominator exists for it)
+    compute = {k: {"ms": kernel_ms[k], "gflop": v / 1e9, "tflops": v / (kernel_ms[k] * 1e-3) / 1e12,
+                   "frac_of_nominal_fp32_peak": v / (kernel_ms[k] * 1e-3) / 1e12 / fp32_peak} for k, v in flops.items()}
     out = {
         "metric": METRIC, "value": world * N * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -328,12 +341,15 @@ def run_native(args, rank, world):
         "config": {"workload": WORKLOAD, "envs_per_gpu": N, "depth": [H, W], "grid": G, "frames_rotated": FRAMES,
                    "l2": "per-step working set (prob+scanned+gt grids 0.8 GB, observations 0.28 GB, conv1 activations 0.49 GB) "
                          "exceeds the 126 MB L2; no explicit flush",
-                   "stages_ms": stages},
+                   "stages_ms": stages, "encoder_kernel_ms_last_step": kernel_ms},
         "roofline": {"bound": "hbm", "kernel": "grid_update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": 1569.4e6,
                      "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_grid,
                      "voxelize_algorithmic_bytes_per_step": N * (b_vox + b_cov)},
+        "compute_kernels": {"note": "fp32 CUDA-core contractions (1e-4 parity budget rules out bf16/tf32 operands); nominal "
+                                    "fp32 peak %.1f TFLOP/s; tensor-pipe utilisation is 0 by design this round" % fp32_peak,
+                            "kernels": compute},
         "e2e": {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},
         "gpu_launches": (launches or 0) * K, "gpu_launches_per_step": launches,

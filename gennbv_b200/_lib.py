@@ -35,6 +35,8 @@ class EncoderGrads(ctypes.Structure):
 SIGNATURES = {
     "gnbv_abi_version": (c_int, []),
     "gnbv_last_error": (ctypes.c_char_p, []),
+    "gnbv_profile_enable": (c_int, [c_int]),
+    "gnbv_profile_elapsed_ms": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
     "gnbv_voxelize_workspace_bytes": (c_size_t, [c_int, c_int]),
     "gnbv_voxelize_step": (c_int, [c_void_p] * 11 + [c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
                                                       c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
@@ -42,6 +44,8 @@ SIGNATURES = {
     "gnbv_grid_update": (c_int, [c_void_p] * 4 + [c_int64, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "gnbv_voxelize_masks": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                                     ctypes.POINTER(c_int64)]),
+    "gnbv_points_to_voxel_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "gnbv_bresenham_rays": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gnbv_reset_grids": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "gnbv_actions_to_poses": (c_int, [c_void_p] * 9 + [c_int, c_int, c_void_p]),
     "gnbv_obs_update": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_int] * 8 + [c_void_p]),
@@ -95,3 +99,17 @@ def check(rc, what):
     if rc != 0:
         msg = lib().gnbv_last_error().decode(errors="replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+# stage ids of include/gennbv_b200.h (each marks the START of the named stage)
+ENCODER_STAGES = {"fwd.action_mlp": (0, 1), "fwd.conv1": (1, 2), "fwd.bn1_stats": (2, 3), "fwd.conv2": (3, 4),
+                  "fwd.bn2_stats+apply": (4, 5), "fwd.grid_fc": (5, 6), "fwd.out_fc": (6, 7),
+                  "bwd.linear_layers": (16, 17), "bwd.grid_fc": (17, 18), "bwd.bn2": (18, 19), "bwd.conv2_wgrad": (19, 20),
+                  "bwd.conv2_dgrad": (20, 21), "bwd.bn1_stats": (21, 22), "bwd.conv1_wgrad": (22, 23)}
+
+
+def stage_ms(name):
+    a, b = ENCODER_STAGES[name]
+    out = c_float()
+    check(lib().gnbv_profile_elapsed_ms(a, b, ctypes.byref(out)), "gnbv_profile_elapsed_ms")
+    return out.value

@@ -10,6 +10,7 @@
 namespace gnbv {
 
 void set_error(const char* fmt, ...);
+void stage_mark(int id, cudaStream_t stream);      // no-op unless gnbv_profile_enable(1)
 
 #define GNBV_REQUIRE(cond, ...)                 \
     do {                                        \

@@ -889,6 +889,7 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     GemmEpilogue relu_ep;
     relu_ep.relu = 1;
     int rc;
+    stage_mark(GNBV_ST_FWD_ACTION_MLP, stream);
     // ---- action branch: positional encoding -> Linear(4S,256)+ReLU -> Linear(256,256)+ReLU (written into cat[:, :256])
     posenc_kernel<<<(unsigned)ceil_div((int64_t)B * d.S, 256), 256, 0, stream>>>(obs, obs_row_stride, row_index, ws + w.pe, B, d.S);
     GNBV_LAUNCH_CHECK("posenc_kernel");
@@ -899,10 +900,12 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     rc = launch_gemm(ws + w.h1, d.HID, 1, p->act_fc2_w, 1, d.HID, ws + w.cat, 2 * d.HID, B, d.HID, d.HID, relu_ep, ws + w.gemm, stream);
     if (rc) return rc;
     // ---- grid branch
+    stage_mark(GNBV_ST_FWD_CONV1, stream);
     float* part1 = training ? ws + w.part1 : nullptr;
     conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
                                                                       ws + w.y1, part1, d.G, d.G1);
     GNBV_LAUNCH_CHECK("conv1_fwd_kernel");
+    stage_mark(GNBV_ST_FWD_BN1, stream);
     if (training) {
         const int nm = (int)ceil_div((int64_t)B * d.nblk1, MERGE_FAN);
         bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part1, B * d.nblk1, ws + w.merge1);
@@ -912,10 +915,12 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     else
         bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, ws + w.stat1, 1e-5f);
     GNBV_LAUNCH_CHECK("bn1 statistics");
+    stage_mark(GNBV_ST_FWD_CONV2, stream);
     float* part2 = training ? ws + w.part2 : nullptr;
     conv2_fwd_kernel<<<dim3(d.nblk2, B), CONV2_THREADS, 0, stream>>>(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2,
                                                                       part2, d.G1, d.G2);
     GNBV_LAUNCH_CHECK("conv2_fwd_kernel");
+    stage_mark(GNBV_ST_FWD_BN2, stream);
     if (training) {
         const int nm = (int)ceil_div((int64_t)B * d.nblk2, MERGE_FAN);
         bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part2, B * d.nblk2, ws + w.merge2);
@@ -929,14 +934,18 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     bn_relu_apply_kernel<<<(unsigned)ceil_div(tot2, 256), 256, 0, stream>>>(ws + w.y2, ws + w.stat2, ws + w.act2, tot2, d.P2);
     GNBV_LAUNCH_CHECK("bn_relu_apply_kernel");
     // Linear(16*G2^3, 256)+ReLU -> cat[:, 256:512]
+    stage_mark(GNBV_ST_FWD_GRID_FC, stream);
     relu_ep.bias = p->grid_fc_b;
     rc = launch_gemm(ws + w.act2, d.flat2, 1, p->grid_fc_w, 1, d.flat2, ws + w.cat + d.HID, 2 * d.HID, B, d.HID, (int)d.flat2,
                      relu_ep, ws + w.gemm, stream);
     if (rc) return rc;
     // fuse: Linear(512,256)+ReLU -> features
+    stage_mark(GNBV_ST_FWD_OUT_FC, stream);
     relu_ep.bias = p->out_fc_b;
-    return launch_gemm(ws + w.cat, 2 * d.HID, 1, p->out_fc_w, 1, 2 * d.HID, features, d.FEAT, B, d.FEAT, 2 * d.HID, relu_ep,
-                       ws + w.gemm, stream);
+    rc = launch_gemm(ws + w.cat, 2 * d.HID, 1, p->out_fc_w, 1, 2 * d.HID, features, d.FEAT, B, d.FEAT, 2 * d.HID, relu_ep,
+                     ws + w.gemm, stream);
+    stage_mark(GNBV_ST_FWD_END, stream);
+    return rc;
 }
 
 extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
@@ -959,6 +968,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     GemmEpilogue none;
     int rc;
     auto blocks = [](int64_t n) { return (unsigned)ceil_div(n, 256); };
+    stage_mark(GNBV_ST_BWD_LINEAR, stream);
     // ---- fuse layer: features = relu(cat W^T + b)
     relu_mask_kernel<<<blocks((int64_t)B * d.FEAT), 256, 0, stream>>>(dfeatures, d.FEAT, ws + w.dz, d.FEAT, features, d.FEAT, B, d.FEAT);
     GNBV_LAUNCH_CHECK("relu_mask_kernel");
@@ -979,6 +989,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     if (rc) return rc;
     colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dh1, H, B, H, gr->act_fc1_b);
     // ---- grid branch: Linear
+    stage_mark(GNBV_ST_BWD_GRID_FC, stream);
     const float* dcat_g = ws + w.dcat + H;
     rc = launch_gemm(dcat_g, 1, 2 * H, ws + w.act2, d.flat2, 1, gr->grid_fc_w, d.flat2, H, (int)d.flat2, B, none, ws + w.gemm, stream);
     if (rc) return rc;
@@ -987,6 +998,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     if (rc) return rc;
     GNBV_LAUNCH_CHECK("linear backward");
     // ---- BN2 + ReLU backward
+    stage_mark(GNBV_ST_BWD_BN2, stream);
     bn2_bwd_reduce_kernel<<<dim3(C1, B), 256, 0, stream>>>(ws + w.dact2, ws + w.act2, ws + w.y2, ws + w.stat2, ws + w.bn2part, d.P2);
     bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bn2part, B, 2 * C1, 0, (double)B * d.P2, gr->bn2_w, gr->bn2_b,
                                                       ws + w.coef2, training ? 0 : 1);
@@ -994,6 +1006,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
                                                                                       ws + w.stat2, ws + w.coef2, ws + w.dy2cl, d.P2);
     GNBV_LAUNCH_CHECK("bn2 backward");
     // ---- conv2 backward
+    stage_mark(GNBV_ST_BWD_CONV2_WGRAD, stream);
     const size_t smem_wg2 = 3 * (size_t)WG2_REC * 4;
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
     conv2_wgrad_kernel<<<w.nblk_wg2, WG2_THREADS, smem_wg2, stream>>>(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, d.G1,
@@ -1001,9 +1014,11 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);
+    stage_mark(GNBV_ST_BWD_CONV2_DGRAD, stream);
     conv2_dgrad_kernel<<<dim3(w.nblk_dg, B), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1,
                                                                         ws + w.bpart1, d.G1, d.G2);
     GNBV_LAUNCH_CHECK("conv2_dgrad_kernel");
+    stage_mark(GNBV_ST_BWD_BN1, stream);
     {
         const int nm = (int)ceil_div((int64_t)B * w.nblk_dg, MERGE_FAN);
         sum_merge_kernel<<<nm, 32 * C1, 0, stream>>>(ws + w.bpart1, B * w.nblk_dg, ws + w.bmerge1);
@@ -1011,11 +1026,13 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
                                                           ws + w.coef1, training ? 0 : 1);
     }
     // ---- conv1 backward (weights only: the input is data)
+    stage_mark(GNBV_ST_BWD_CONV1_WGRAD, stream);
     const int vec1 = (d.G % 4 == 0) && (obs_row_stride % 4 == 0) && (state_dim % 4 == 0) && (((uintptr_t)obs & 15) == 0);
     conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
                                                                 ws + w.coef1, ws + w.wg1part, d.G, d.G1, w.wg1_items, w.wg1_ips, vec1);
     GNBV_LAUNCH_CHECK("conv1_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, w.nblk_wg1, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
     GNBV_LAUNCH_CHECK("reduce_records_kernel");
+    stage_mark(GNBV_ST_BWD_END, stream);
     return GNBV_OK;
 }

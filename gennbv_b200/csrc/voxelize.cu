@@ -387,6 +387,63 @@ reset_grids_kernel(float* __restrict__ prob, float* __restrict__ scan, const uin
     }
 }
 
+
+// ---- compatibility kernels behind the reference's free functions (gennbv/utils.py) -------------------------------
+// scanned_pts_to_idx_3D (utils.py:230-270) for one env given explicit world points: OR the voxel bit of every point
+// strictly inside the grid volume (clamped index), mask[words] must be zeroed by the caller.
+__global__ void points_to_mask_kernel(const float* __restrict__ pts, int64_t n, const float* __restrict__ range6,
+                                      const float* __restrict__ vs3, uint32_t* __restrict__ mask, int G) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int idx[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float vs = vs3[a];
+        const float hi = __fadd_rn(range6[2 * a], __fmul_rn(0.5f, vs)), lo = __fsub_rn(range6[2 * a + 1], __fmul_rn(0.5f, vs));
+        const float w = pts[i * 3 + a];
+        if (!(hi > w && w > lo)) return;
+        int k = (int)floorf(__fdiv_rn(__fsub_rn(w, lo), vs));
+        idx[a] = max(0, min(G - 1, k));
+    }
+    const int lin = (idx[0] * G + idx[1]) * G + idx[2];
+    atomicOr(&mask[lin >> 5], 1u << (lin & 31));
+}
+
+// bresenham3D_pycuda (utils.py:24-227), two passes so that the concatenated output keeps the reference's layout
+// (ray order, duplicates kept): pass 0 counts the in-bounds voxels of each ray, pass 1 writes them at offsets[ray].
+__global__ void bresenham_rays_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t num_rays,
+                                      int G, int64_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                      int64_t* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_rays) return;
+    const int x0 = src[0], y0 = src[1], z0 = src[2], x1 = tgt[r * 3], y1 = tgt[r * 3 + 1], z1 = tgt[r * 3 + 2];
+    const int dx = abs(x1 - x0), dy = abs(y1 - y0), dz = abs(z1 - z0);
+    const int sx = x0 < x1 ? 1 : -1, sy = y0 < y1 ? 1 : -1, sz = z0 < z1 ? 1 : -1;
+    const int dm = max(dx, max(dy, dz));
+    int x = x0, y = y0, z = z0, p1, p2, dmaj, d1, d2;
+    int axis = dm == dx ? 0 : (dm == dy ? 1 : 2);                      // tie-break dx -> dy -> dz (utils.py:69,102,133)
+    if (axis == 0) { dmaj = dx; d1 = dy; d2 = dz; } else if (axis == 1) { dmaj = dy; d1 = dx; d2 = dz; } else { dmaj = dz; d1 = dx; d2 = dy; }
+    p1 = 2 * d1 - dmaj; p2 = 2 * d2 - dmaj;
+    int64_t n = 0;
+    int64_t* o = out ? out + offsets[r] * 3 : nullptr;
+    const int cap = 3 * G;
+    auto emit = [&]() {
+        if ((unsigned)x < (unsigned)G && (unsigned)y < (unsigned)G && (unsigned)z < (unsigned)G) {
+            if (o) { o[n * 3] = x; o[n * 3 + 1] = y; o[n * 3 + 2] = z; }
+            ++n;
+        }
+    };
+    emit();
+    for (int i = 0; i < dmaj && n < cap; ++i) {
+        if (axis == 0) { if (p1 >= 0) { y += sy; p1 -= 2 * dmaj; } if (p2 >= 0) { z += sz; p2 -= 2 * dmaj; } x += sx; }
+        else if (axis == 1) { if (p1 >= 0) { x += sx; p1 -= 2 * dmaj; } if (p2 >= 0) { z += sz; p2 -= 2 * dmaj; } y += sy; }
+        else { if (p1 >= 0) { x += sx; p1 -= 2 * dmaj; } if (p2 >= 0) { y += sy; p2 -= 2 * dmaj; } z += sz; }
+        p1 += 2 * d1; p2 += 2 * d2;
+        emit();
+    }
+    if (counts) counts[r] = n;
+}
+
 }  // namespace gnbv
 
 using namespace gnbv;
@@ -490,5 +547,27 @@ extern "C" int gnbv_reset_grids(float* prob_grid, float* scanned_gt, const uint8
     const int vec_ok = (V % 4 == 0) && (((uintptr_t)prob_grid | (uintptr_t)scanned_gt) & 15) == 0;
     reset_grids_kernel<<<grid, 256, 0, stream>>>(prob_grid, scanned_gt, reset_flags, (int)V, vec_ok);
     GNBV_LAUNCH_CHECK("reset_grids_kernel");
+    return GNBV_OK;
+}
+
+extern "C" int gnbv_points_to_voxel_mask(const float* points, int64_t num_points, const float* range_gt6,
+                                         const float* voxel_size3, uint32_t* mask, int G, void* stream) {
+    GNBV_REQUIRE(range_gt6 && voxel_size3 && mask && G > 0 && num_points >= 0 && (points || num_points == 0),
+                 "gnbv_points_to_voxel_mask: bad arguments");
+    if (num_points == 0) return GNBV_OK;
+    points_to_mask_kernel<<<(unsigned)ceil_div(num_points, 256), 256, 0, (cudaStream_t)stream>>>(points, num_points, range_gt6,
+                                                                                               voxel_size3, mask, G);
+    GNBV_LAUNCH_CHECK("points_to_mask_kernel");
+    return GNBV_OK;
+}
+
+extern "C" int gnbv_bresenham_rays(const int32_t* source3, const int32_t* targets, int64_t num_rays, int G, int64_t* counts,
+                                   const int64_t* offsets, int64_t* out, void* stream) {
+    GNBV_REQUIRE(source3 && G > 0 && num_rays >= 0 && (targets || num_rays == 0) && (counts || (offsets && out)),
+                 "gnbv_bresenham_rays: bad arguments");
+    if (num_rays == 0) return GNBV_OK;
+    bresenham_rays_kernel<<<(unsigned)ceil_div(num_rays, 256), 256, 0, (cudaStream_t)stream>>>(source3, targets, num_rays, G,
+                                                                                             counts, offsets, out);
+    GNBV_LAUNCH_CHECK("bresenham_rays_kernel");
     return GNBV_OK;
 }

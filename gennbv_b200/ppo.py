@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
+from . import dist as gdist
 from .buffers import TensorRolloutBuffer_Grid_Obs
 from .policy import ActorCriticPolicy_Train_Eval
 
@@ -84,10 +85,7 @@ class PPO_Grid_Obs:
         self._adam_step = 0
         self._clip_ws = torch.zeros(_lib.lib().gnbv_clip_adam_workspace_bytes() // 4, device=self.device)
         self._scalars = torch.zeros(8, device=self.device)
-        if self.world_size > 1:                               # identical replicas: broadcast rank 0's parameters + BN buffers
-            torch.distributed.broadcast(self.policy.flat_params, 0)
-            for b in self.policy.buffers():
-                torch.distributed.broadcast(b, 0)
+        gdist.broadcast_state_(self.policy.flat_params, list(self.policy.buffers()))   # identical replicas
 
     # ---------------------------------------------------------------------------------------------------- rollouts
     def _setup_learn(self):
@@ -165,9 +163,7 @@ class PPO_Grid_Obs:
         enc._run_backward(buf.flat("observations"), w["feats"], w["dfeat"], B, True, ws, row_index=rows, grads=self._enc_grads)
         n = pol.flat_grads.numel()
         grad_scale = 1.0
-        if self.world_size > 1:
-            torch.distributed.all_reduce(pol.flat_grads)             # NCCL over NVLink, one flat bucket
-            pol.flat_grads.mul_(1.0 / self.world_size)               # mean over ranks before the global-norm clip
+        gdist.allreduce_mean_(pol.flat_grads)                        # NCCL over NVLink, one flat bucket, before the clip
         _lib.check(L.gnbv_grad_norm(pol.flat_grads.data_ptr(), n, float(self.max_grad_norm), self._clip_ws.data_ptr(), s),
                    "gnbv_grad_norm")
         self._adam_step += 1
@@ -195,20 +191,16 @@ class PPO_Grid_Obs:
         clip_range_vf = None if self.clip_range_vf is None else self.clip_range_vf(self._current_progress_remaining)
         log = []                       # per-minibatch device scalars, read back once at the end
         continue_training = True
-        kl_buf = torch.zeros(1, device=self.device)
         for epoch in range(self.n_epochs):
             for rows in self.rollout_buffer.minibatch_rows(self.batch_size):
                 w, ws, actions = self._minibatch_update(rows, clip_range, clip_range_vf)
                 log.append(self._scalars.clone())
-                if self.target_kl is not None:
-                    kl_buf.copy_(self._scalars[4:5])
-                    if self.world_size > 1:
-                        torch.distributed.all_reduce(kl_buf, op=torch.distributed.ReduceOp.MAX)
-                    if float(kl_buf) > 1.5 * self.target_kl:          # one host read per minibatch, as the reference (:259-268)
-                        continue_training = False
-                        if self.verbose >= 1:
-                            print(f"Early stopping at step {epoch} due to reaching max kl: {float(kl_buf):.2f}")
-                        break
+                # one host read per minibatch, as the reference (:259-268); MAX over ranks keeps the ranks in lock-step
+                if gdist.should_stop(self._scalars[4:5], self.target_kl):
+                    continue_training = False
+                    if self.verbose >= 1:
+                        print(f"Early stopping at step {epoch} due to reaching max kl")
+                    break
                 self._minibatch_backward_and_step(rows, w, ws, actions)
             if not continue_training:
                 break

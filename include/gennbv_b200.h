@@ -32,6 +32,21 @@ extern "C" {
 int gnbv_abi_version(void);
 const char* gnbv_last_error(void);
 
+/* ---- optional stage timing (measurement aid, not on the reference's API surface) ----
+ * After gnbv_profile_enable(1) the multi-kernel entry points record a CUDA event on their stream at every stage
+ * boundary; gnbv_profile_elapsed_ms(a, b) synchronises on event b and returns the device time between stages a and b.
+ * Encoder stage ids: forward GNBV_ST_FWD_BEGIN .. GNBV_ST_FWD_END, backward GNBV_ST_BWD_BEGIN .. GNBV_ST_BWD_END
+ * (each id marks the START of the named stage). */
+#define GNBV_MAX_STAGES 48
+enum {
+    GNBV_ST_FWD_BEGIN = 0, GNBV_ST_FWD_ACTION_MLP = 0, GNBV_ST_FWD_CONV1 = 1, GNBV_ST_FWD_BN1 = 2, GNBV_ST_FWD_CONV2 = 3,
+    GNBV_ST_FWD_BN2 = 4, GNBV_ST_FWD_GRID_FC = 5, GNBV_ST_FWD_OUT_FC = 6, GNBV_ST_FWD_END = 7,
+    GNBV_ST_BWD_BEGIN = 16, GNBV_ST_BWD_LINEAR = 16, GNBV_ST_BWD_GRID_FC = 17, GNBV_ST_BWD_BN2 = 18, GNBV_ST_BWD_CONV2_WGRAD = 19,
+    GNBV_ST_BWD_CONV2_DGRAD = 20, GNBV_ST_BWD_BN1 = 21, GNBV_ST_BWD_CONV1_WGRAD = 22, GNBV_ST_BWD_END = 23
+};
+int gnbv_profile_enable(int on);
+int gnbv_profile_elapsed_ms(int stage_from, int stage_to, float* ms);
+
 /* ---- flags for gnbv_voxelize_step ---- */
 #define GNBV_RAW_DEPTH 1u   /* depth is the raw sensor image: apply post_process_camera_tensor's chain first */
 
@@ -93,6 +108,18 @@ int gnbv_grid_update(const float* grid_gt, float* prob_grid, float* scanned_gt,
  * words_per_env receives the row pitch in u32 words. Returned pointers alias `workspace`. */
 int gnbv_voxelize_masks(void* workspace, int num_envs, int grid_size,
                         const uint32_t** target_mask, const uint32_t** touched_mask, int64_t* words_per_env);
+
+/* Kernels behind the reference's free functions, for callers that use them outside the env (gennbv/utils.py):
+ *   gnbv_points_to_voxel_mask : scanned_pts_to_idx_3D (utils.py:230-270) for ONE env from explicit world points
+ *       [num_points,3] f32: ORs bit (x*G+y)*G+z of `mask` (ceil(G^3/32) u32 words, zeroed by the caller) for every point
+ *       strictly inside the grid volume; the set bits in increasing order are the unique, clamped, sorted index rows.
+ *   gnbv_bresenham_rays : bresenham3D_pycuda (utils.py:24-227).  Call once with counts != NULL (out = NULL) to get the
+ *       per-ray number of in-bounds voxels, exclusive-scan them into offsets, call again with out [sum,3] i64: rows
+ *       are written in ray order, duplicates kept, exactly the reference's concatenated trajectory. source3 / targets i32. */
+int gnbv_points_to_voxel_mask(const float* points, int64_t num_points, const float* range_gt6, const float* voxel_size3,
+                              uint32_t* mask, int grid_size, void* stream);
+int gnbv_bresenham_rays(const int32_t* source3, const int32_t* targets, int64_t num_rays, int grid_size, int64_t* counts,
+                        const int64_t* offsets, int64_t* out, void* stream);
 
 /* reset_idx's grid part (env_train_gennbv.py:413-417): zero prob_grid / scanned_gt rows whose
  * reset flag is non-zero.  reset_flags [N] u8 on device -- no host round trip. */
