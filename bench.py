@@ -246,9 +246,9 @@ def run_native(args, rank, world):
         step(i)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(K)]
     sampler = ClockSampler(local)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()           # before the barrier: its start-up sleep must not skew rank 0 against the others
+    barrier()
     from gennbv_b200 import _lib
     _lib.check(_lib.lib().gnbv_profile_enable(1), "gnbv_profile_enable")      # stage events inside the encoder calls
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -267,19 +267,22 @@ def run_native(args, rank, world):
     _lib.lib().gnbv_profile_enable(0)
     env._gym_env.profile_events = None
     stage = lambda a, b: float(np.mean([e[a].elapsed_time(e[b]) for e in ev]))
+    per_step = np.array([e[0].elapsed_time(e[6]) for e in ev])
+    step_spread = {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())}
     stages = {"env.step total": stage(0, 4), "scan_raycast": stage(1, 2), "grid_update+coverage": stage(2, 3),
               "encoder_forward": stage(4, 5), "encoder_backward(+allreduce)": stage(5, 6)}
     # kernel launches of one step, counted with the CUDA profiler (every kernel of libgennbv_b200 lives in namespace gnbv)
+    # (every rank runs this extra step: it contains the gradient all-reduce, which must stay matched across ranks)
     launches = None
-    if rank == 0:
-        try:
-            from torch.profiler import ProfilerActivity, profile
-            with profile(activities=[ProfilerActivity.CUDA]) as prof:
-                step(Wm + K)
-                torch.cuda.synchronize()
-            launches = sum(1 for e in prof.events() if "gnbv::" in e.name)
-        except Exception:
-            launches = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(Wm + K)
+            torch.cuda.synchronize()
+        launches = sum(1 for e in prof.events() if "gnbv::" in e.name)
+    except ImportError:
+        step(Wm + K)
+        torch.cuda.synchronize()
     del step, env, sensor, policy
     torch.cuda.empty_cache()
 
@@ -341,7 +344,7 @@ def run_native(args, rank, world):
         "config": {"workload": WORKLOAD, "envs_per_gpu": N, "depth": [H, W], "grid": G, "frames_rotated": FRAMES,
                    "l2": "per-step working set (prob+scanned+gt grids 0.8 GB, observations 0.28 GB, conv1 activations 0.49 GB) "
                          "exceeds the 126 MB L2; no explicit flush",
-                   "stages_ms": stages, "encoder_kernel_ms_last_step": kernel_ms},
+                   "stages_ms": stages, "step_ms_spread": step_spread, "encoder_kernel_ms_last_step": kernel_ms},
         "roofline": {"bound": "hbm", "kernel": "grid_update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": 1569.4e6,
                      "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
