@@ -149,6 +149,12 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
     C[(int64_t)m * ldc + n] = v;
 }
 
+void launch_splitk_reduce(const float* ws, float* C, int64_t ldc, int M, int N, int splits, const float* bias, int relu,
+                          cudaStream_t stream) {
+    int64_t total = (int64_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(ws, C, ldc, M, N, splits, bias, relu);
+}
+
 static void pick_splits(int M, int N, int K, int& splits, int& Kc) {
     int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
     int64_t want = std::max<int64_t>(1, ceil_div(2 * 148, tiles));

@@ -30,4 +30,11 @@ size_t gemm_workspace_floats(int M, int N, int K);
 int launch_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* C,
                 int64_t ldc, int M, int N, int K, const GemmEpilogue& ep, float* workspace, cudaStream_t stream);
 
+// Split-precision (3xTF32) tcgen05 version of the same contract (tc_gemm.cu).  `workspace` must hold
+// tc_gemm_workspace_floats(M,N,K) floats and be zero-initialised once (its first 64 floats carry a sticky error flag set
+// if a bounded mbarrier wait ever expires).
+size_t tc_gemm_workspace_floats(int M, int N, int K);
+int launch_tc_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* C,
+                   int64_t ldc, int M, int N, int K, const GemmEpilogue& ep, float* workspace, cudaStream_t stream);
+
 }  // namespace gnbv

@@ -1,0 +1,241 @@
+// tc_gemm.cu -- split-precision (3xTF32) tcgen05 GEMM: C[M,N] = epilogue(A * B) with fp32-grade accuracy on the
+// 5th-generation tensor cores (see tc.cuh for the numerics and the shared-memory layout).
+//
+// One CTA = one 128 x BN output tile over one K split.  256 threads stage A and B tiles (arbitrary strides, either
+// dimension contiguous) from global memory into the canonical UMMA layout, splitting every value into (hi, lo) on the
+// way; one elected thread issues 3 x BK/8 tcgen05.mma per stage into a TMEM accumulator (128 lanes x BN columns);
+// two shared-memory stages overlap the loads of stage i+1 with the MMAs of stage i (tcgen05.commit -> mbarrier);
+// warps 0-3 read the accumulator back with tcgen05.ld and store either the final tile (bias / ReLU fused) or a split-K
+// partial that splitk_reduce_kernel (gemm.cu) sums in a fixed order.
+#include "gemm.cuh"
+#include "tc.cuh"
+
+#include <algorithm>
+
+namespace gnbv {
+
+constexpr int TC_BM = 128;
+constexpr int TC_THREADS = 256;
+
+struct TcGemmArgs {
+    const float* A; int64_t sa_m, sa_k;
+    const float* B; int64_t sb_k, sb_n;
+    float* C; int64_t ldc;
+    float* ws;
+    int M, N, K, Kc, splits;
+    const float* bias; int relu;
+    int vecA, vecB;
+    int* err;
+};
+
+// Stage an [R x BK] operand tile (rows r0.., K range k0..) into smem as (hi, lo) K-major tiles.
+// MODE 0: K contiguous in global (element (r,k) at base[r*ld_r + k]); MODE 1: rows contiguous (base[r + k*ld_k]).
+template <int R, int MODE>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ base, int64_t ld, int r0, int rows, int k0, int k_end,
+                                           bool vec, uint8_t* hi, uint8_t* lo) {
+    const int t = threadIdx.x;
+    if (MODE == 0) {
+        for (int u = t; u < R * (tc::BK / 4); u += TC_THREADS) {
+            const int r_low = u & 7, k4 = (u >> 3) & 7, r = (u >> 6) * 8 + r_low;
+            const int gr = r0 + r, gk = k0 + k4 * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < rows) {
+                const float* p = base + (int64_t)gr * ld + gk;
+                if (vec && gk + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    if (gk < k_end) v.x = __ldg(p);
+                    if (gk + 1 < k_end) v.y = __ldg(p + 1);
+                    if (gk + 2 < k_end) v.z = __ldg(p + 2);
+                    if (gk + 3 < k_end) v.w = __ldg(p + 3);
+                }
+            }
+            float4 h, l;
+            tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+            const uint32_t off = tc::tile_offset(r, k4 * 4);
+            *reinterpret_cast<float4*>(hi + off) = h;
+            *reinterpret_cast<float4*>(lo + off) = l;
+        }
+    } else {
+        for (int u = t; u < (R / 4) * tc::BK; u += TC_THREADS) {
+            const int r4 = u % (R / 4), k = u / (R / 4);
+            const int gr = r0 + r4 * 4, gk = k0 + k;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < k_end) {
+                const float* p = base + (int64_t)gk * ld + gr;
+                if (vec && gr + 3 < rows) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    if (gr < rows) v.x = __ldg(p);
+                    if (gr + 1 < rows) v.y = __ldg(p + 1);
+                    if (gr + 2 < rows) v.z = __ldg(p + 2);
+                    if (gr + 3 < rows) v.w = __ldg(p + 3);
+                }
+            }
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float h, l;
+                tc::split_tf32(x[e], h, l);
+                const uint32_t off = tc::tile_offset(r4 * 4 + e, k);
+                *reinterpret_cast<float*>(hi + off) = h;
+                *reinterpret_cast<float*>(lo + off) = l;
+            }
+        }
+    }
+}
+
+template <int BN, int A_MODE, int B_MODE>   // A_MODE 0: k contiguous, 1: m contiguous.  B_MODE 0: n contiguous, 1: k contiguous
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(TcGemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr uint32_t A_TILE = TC_BM * tc::BK * 4, B_TILE = BN * tc::BK * 4, STAGE = 2 * A_TILE + 2 * B_TILE;
+    __shared__ __align__(8) uint64_t mbar[3];             // [0], [1]: stage free; [2]: accumulator complete
+    __shared__ uint32_t tmem_base_smem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN, z = blockIdx.z;
+    const int k_begin = z * g.Kc, k_end = min(g.K, k_begin + g.Kc);
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (tid == 0) {
+        tc::mbar_init(tc::smem_u32(&mbar[0]), 1);
+        tc::mbar_init(tc::smem_u32(&mbar[1]), 1);
+        tc::mbar_init(tc::smem_u32(&mbar[2]), 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tc::smem_u32(&tmem_base_smem), TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+    const uint32_t idesc = tc::make_idesc_tf32(TC_BM, BN);
+
+    const int nstages = (k_end - k_begin + tc::BK - 1) / tc::BK;
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    for (int s = 0; s < nstages; ++s) {
+        const int buf = s & 1, k0 = k_begin + s * tc::BK;
+        uint8_t* st = smem + buf * STAGE;
+        // the MMAs that read this buffer two stages ago must have completed
+        if (s >= 2) { ok = tc::mbar_wait(tc::smem_u32(&mbar[buf]), phase[buf]) && ok; phase[buf] ^= 1; }
+        if (A_MODE == 0) stage_tile<TC_BM, 0>(g.A, g.sa_m, m0, g.M, k0, k_end, g.vecA, st, st + A_TILE);
+        else             stage_tile<TC_BM, 1>(g.A, g.sa_k, m0, g.M, k0, k_end, g.vecA, st, st + A_TILE);
+        if (B_MODE == 1) stage_tile<BN, 0>(g.B, g.sb_n, n0, g.N, k0, k_end, g.vecB, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE);
+        else             stage_tile<BN, 1>(g.B, g.sb_k, n0, g.N, k0, k_end, g.vecB, st + 2 * A_TILE, st + 2 * A_TILE + B_TILE);
+        tc::fence_async_smem();                 // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        __syncthreads();
+        if (tid == 0) {
+            tc::tc_fence_after();
+            const uint32_t a_hi = tc::smem_u32(st), a_lo = a_hi + A_TILE, b_hi = a_hi + 2 * A_TILE, b_lo = b_hi + B_TILE;
+            tc::mma_stage_3xtf32(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, s == 0);
+            tc::mma_commit(tc::smem_u32(&mbar[buf]));
+            if (s == nstages - 1) tc::mma_commit(tc::smem_u32(&mbar[2]));
+        }
+    }
+    // ---- epilogue: wait for the accumulator, TMEM -> registers -> global
+    if (nstages > 0) ok = tc::mbar_wait(tc::smem_u32(&mbar[2]), 0) && ok;
+    tc::tc_fence_after();
+    if (!ok && tid == 0 && g.err) atomicExch(g.err, 1);
+    if (warp < 4 && nstages > 0) {
+        const int m = m0 + warp * 32 + lane;
+        const uint32_t trow = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            tc::tmem_ld16(trow + c, v);
+            if (m < g.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c + j;
+                    if (n < g.N) {
+                        float x = v[j];
+                        if (g.splits == 1) {
+                            if (g.bias) x += __ldg(g.bias + n);
+                            if (g.relu) x = fmaxf(x, 0.f);
+                            g.C[(int64_t)m * g.ldc + n] = x;
+                        } else {
+                            g.ws[((int64_t)z * g.M + m) * g.N + n] = x;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, TMEM_COLS);
+}
+
+// split-K reduction kernel lives in gemm.cu
+void launch_splitk_reduce(const float* ws, float* C, int64_t ldc, int M, int N, int splits, const float* bias, int relu,
+                          cudaStream_t stream);
+
+static void tc_pick_splits(int M, int N, int K, int BN, int& splits, int& Kc) {
+    int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
+    int64_t want = std::max<int64_t>(1, ceil_div(148, tiles));
+    int64_t max_splits = std::max<int64_t>(1, K / 256);          // at least 8 stages per split
+    splits = (int)std::min(want, max_splits);
+    Kc = (int)(ceil_div(ceil_div(K, splits), tc::BK) * tc::BK);
+    splits = (int)ceil_div(K, Kc);
+}
+
+size_t tc_gemm_workspace_floats(int M, int N, int K) {
+    int s, kc;
+    tc_pick_splits(M, N, K, N >= 256 ? 256 : 64, s, kc);
+    return (s > 1 ? (size_t)s * M * N : 0) + 64;       // + error flag slot
+}
+
+template <int BN>
+static int launch_tc(const TcGemmArgs& g, int a_mode, int b_mode, dim3 grid, cudaStream_t stream) {
+    constexpr size_t smem = 2 * (2 * TC_BM * tc::BK * 4 + 2 * BN * tc::BK * 4);
+#define GNBV_TC_LAUNCH(AM, BMODE)                                                                                        \
+    do {                                                                                                                 \
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, AM, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem));                                                                \
+        tc_gemm_kernel<BN, AM, BMODE><<<grid, TC_THREADS, smem, stream>>>(g);                                            \
+    } while (0)
+    if (a_mode == 0 && b_mode == 0) GNBV_TC_LAUNCH(0, 0);
+    else if (a_mode == 0 && b_mode == 1) GNBV_TC_LAUNCH(0, 1);
+    else if (a_mode == 1 && b_mode == 0) GNBV_TC_LAUNCH(1, 0);
+    else GNBV_TC_LAUNCH(1, 1);
+#undef GNBV_TC_LAUNCH
+    GNBV_LAUNCH_CHECK("tc_gemm_kernel");
+    return GNBV_OK;
+}
+
+int launch_tc_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* C,
+                   int64_t ldc, int M, int N, int K, const GemmEpilogue& ep, float* workspace, cudaStream_t stream) {
+    GNBV_REQUIRE(A && B && C && workspace && M > 0 && N > 0 && K > 0, "tc_gemm: bad arguments (M=%d N=%d K=%d)", M, N, K);
+    GNBV_REQUIRE(sa_k == 1 || sa_m == 1, "tc_gemm: A must be contiguous along m or k");
+    GNBV_REQUIRE(sb_n == 1 || sb_k == 1, "tc_gemm: B must be contiguous along n or k");
+    TcGemmArgs g;
+    g.A = A; g.sa_m = sa_m; g.sa_k = sa_k; g.B = B; g.sb_k = sb_k; g.sb_n = sb_n; g.C = C; g.ldc = ldc;
+    g.M = M; g.N = N; g.K = K; g.bias = ep.bias; g.relu = ep.relu;
+    const int BN = N >= 256 ? 256 : 64;
+    tc_pick_splits(M, N, K, BN, g.splits, g.Kc);
+    g.err = reinterpret_cast<int*>(workspace);           // slot 0..63 of the workspace: sticky error flag (bounded waits)
+    g.ws = workspace + 64;
+    const int a_mode = (sa_k == 1) ? 0 : 1, b_mode = (sb_n == 1) ? 0 : 1;
+    const int64_t lda = a_mode == 0 ? sa_m : sa_k, ldb = b_mode == 0 ? sb_k : sb_n;
+    g.vecA = ((uintptr_t)A % 16 == 0) && (lda % 4 == 0);
+    g.vecB = ((uintptr_t)B % 16 == 0) && (ldb % 4 == 0);
+    dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, TC_BM), (unsigned)g.splits);
+    int rc = BN == 256 ? launch_tc<256>(g, a_mode, b_mode, grid, stream) : launch_tc<64>(g, a_mode, b_mode, grid, stream);
+    if (rc) return rc;
+    if (g.splits > 1) launch_splitk_reduce(g.ws, C, ldc, M, N, g.splits, ep.bias, ep.relu, stream);
+    return GNBV_OK;
+}
+
+}  // namespace gnbv
+
+extern "C" size_t gnbv_tc_gemm_workspace_bytes(int M, int N, int K) { return gnbv::tc_gemm_workspace_floats(M, N, K) * 4; }
+
+extern "C" int gnbv_tc_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n,
+                            float* C, int64_t ldc, int M, int N, int K, const float* bias, int relu, float* workspace,
+                            size_t workspace_bytes, void* stream) {
+    if (workspace_bytes < gnbv::tc_gemm_workspace_floats(M, N, K) * 4) {
+        gnbv::set_error("gnbv_tc_gemm: workspace %zu B too small", workspace_bytes);
+        return GNBV_E_WORKSPACE;
+    }
+    gnbv::GemmEpilogue ep;
+    ep.bias = bias; ep.relu = relu;
+    return gnbv::launch_tc_gemm(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, ep, workspace, (cudaStream_t)stream);
+}

@@ -146,3 +146,16 @@ def sgemm(A, a_strides, B, b_strides, C, M, N, K, bias=None, relu=False, ldc=Non
                       _ptr(bias, torch.float32, "bias"), int(relu), ws.data_ptr() if nbytes else None, nbytes, _stream())
     _lib.check(rc, "gnbv_sgemm")
     return C
+
+
+def tc_gemm(A, a_strides, B, b_strides, C, M, N, K, bias=None, relu=False, ldc=None, workspace=None):
+    """gnbv_tc_gemm: the tcgen05 / 3xTF32 version of sgemm.  Returns the workspace (float slot 0 = sticky error flag)."""
+    L = _lib.lib()
+    nbytes = L.gnbv_tc_gemm_workspace_bytes(M, N, K)
+    if workspace is None or workspace.numel() * 4 < nbytes:
+        workspace = torch.zeros(nbytes // 4, dtype=torch.float32, device=C.device)
+    rc = L.gnbv_tc_gemm(_ptr(A, torch.float32, "A"), a_strides[0], a_strides[1], _ptr(B, torch.float32, "B"), b_strides[0],
+                        b_strides[1], _ptr(C, torch.float32, "C"), N if ldc is None else ldc, M, N, K,
+                        _ptr(bias, torch.float32, "bias"), int(relu), workspace.data_ptr(), workspace.numel() * 4, _stream())
+    _lib.check(rc, "gnbv_tc_gemm")
+    return workspace

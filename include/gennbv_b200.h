@@ -276,6 +276,14 @@ int gnbv_sgemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64
                int64_t ldc, int M, int N, int K, const float* bias, int relu, float* workspace, size_t workspace_bytes,
                void* stream);
 
+/* Same contract as gnbv_sgemm on the tcgen05 tensor cores with split-precision (3xTF32) operands: fp32-grade accuracy
+ * (~1e-6 relative) at tensor-core rate.  workspace: gnbv_tc_gemm_workspace_bytes(M,N,K) bytes, zero-initialised once
+ * (float slot 0 is a sticky error flag). */
+size_t gnbv_tc_gemm_workspace_bytes(int M, int N, int K);
+int gnbv_tc_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* C,
+                 int64_t ldc, int M, int N, int K, const float* bias, int relu, float* workspace, size_t workspace_bytes,
+                 void* stream);
+
 /* TensorRolloutBuffer_Grid_Obs.compute_returns_and_advantage  (stable_baselines3/common/buffers.py:706-724)
  *   rewards, values [T,N] f32; episode_starts [T,N] u8; last_values [N] f32; dones [N] u8
  *   advantages, returns [T,N] f32 out.  gamma / gae_lambda are the Python doubles of the buffer. */
