@@ -388,25 +388,52 @@ bn2_bwd_apply_kernel(const float* __restrict__ dact2, const float* __restrict__ 
 }
 
 // conv2 weight gradient.  dW2[co,ci,tap] = sum_{b,pos} dy2[b,pos,co] * relu(bn1(y1))[b, 2pos+tap, ci].
-// Block = 4 position streams x 64 threads; thread (ci, tg) owns all 16 co for input channel ci and the 7 taps
-// [7tg, 7tg+7) (112 accumulators): per position 4 LDG.128 (dy2, broadcast) + 7 LDG.32 feed 112 FMA.
+//
+// Work unit = one output z-row (b, x2, y2): G2 positions whose 3x3x(2*G2+1) input neighbourhood is nine CONTIGUOUS
+// channels-last z-lines of y1 (G1*64 B each) plus one contiguous dy2 line (G2*64 B).  A block walks a range of rows with
+// a two-stage pipeline: one thread issues ten TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) for row i+1 while
+// all 256 threads reduce row i out of shared memory.  Thread (g, ci, tg): positions z2 = g mod 4, input channel ci, the 7
+// taps [7tg, 7tg+7) x all 16 output channels (112 accumulators): per position 4 LDS.128 (dy2) + 7 LDS.32 feed 112 FMA.
 // Partials: part[blk][6912 + 16] in weight layout [co][ci][tap] followed by db2[16].
 constexpr int WG2_THREADS = 256;
 constexpr int WG2_TT = 7;
 constexpr int WG2_MAX_BLOCKS = 592;
 constexpr int WG2_REC = C1 * C1 * TAPS + C1;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait_parity(uint32_t mbar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 26); ++it) {          // bounded: a lost copy must not hang the GPU
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(WG2_THREADS)
 conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
-                   float* __restrict__ part, int G1, int G2, int64_t total_pos, int pos_per_stream) {
-    extern __shared__ float sred[];           // [3][WG2_REC] for the cross-stream reduction
-    const int tid = threadIdx.x, stream = tid >> 6, t64 = tid & 63, ci = t64 >> 2, tg = t64 & 3;
+                   float* __restrict__ part, int G1, int G2, int total_rows, int rows_per_block) {
+    extern __shared__ __align__(128) float dsm[];          // [2 stages][9 lines + dy line]  /  later [3][WG2_REC]
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x, g = tid >> 6, t64 = tid & 63, ci = t64 >> 2, tg = t64 & 3;
     const float a1 = stat1[2 * C1 + ci], b1 = stat1[3 * C1 + ci];
     const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    const int LINE = ((G1 * C1 + 31) / 32) * 32;           // floats per staged y1 line (128 B multiple)
+    const int DYL = ((G2 * C1 + 31) / 32) * 32;
+    const int STAGE = 9 * LINE + DYL;
+    const uint32_t line_bytes = (uint32_t)G1 * C1 * 4, dy_bytes = (uint32_t)G2 * C1 * 4;
     int off[WG2_TT];
 #pragma unroll
     for (int tt = 0; tt < WG2_TT; ++tt) {
         const int tap = min(WG2_TT * tg + tt, TAPS - 1);
-        off[tt] = (((tap / 9) * G1 + (tap / 3) % 3) * G1 + tap % 3) * C1;
+        off[tt] = ((tap / 9) * 3 + (tap / 3) % 3) * LINE + (tap % 3) * C1 + ci;       // line (i,j), voxel offset l
     }
     const int ntap = min(WG2_TT, TAPS - WG2_TT * tg);
     float acc[WG2_TT][C1];
@@ -417,32 +444,63 @@ conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1
     float dbs[C1];
 #pragma unroll
     for (int c = 0; c < C1; ++c) dbs[c] = 0.f;
-    const int64_t pos0 = ((int64_t)blockIdx.x * 4 + stream) * pos_per_stream;
-    const int64_t pos1 = min(total_pos, pos0 + pos_per_stream);
-    for (int64_t gp = pos0; gp < pos1; ++gp) {
-        const int b = (int)(gp / P2), p = (int)(gp - (int64_t)b * P2);
-        const int z2 = p % G2, t = p / G2, yy2 = t % G2, x2 = t / G2;
-        const float4* dyp = reinterpret_cast<const float4*>(dy2cl + gp * C1);
-        const float4 d0 = __ldg(dyp), d1 = __ldg(dyp + 1), d2 = __ldg(dyp + 2), d3 = __ldg(dyp + 3);
-        const float dy[C1] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
-        if (t64 == 0) {
+
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(total_rows, r0 + rows_per_block);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int row, int stage) {                  // executed by thread 0 only
+        const int b = row / (G2 * G2), rem = row - b * G2 * G2, x2 = rem / G2, yy2 = rem - x2 * G2;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * STAGE);
+        mbar_expect_tx(bar, 9 * line_bytes + dy_bytes);
 #pragma unroll
-            for (int c = 0; c < C1; ++c) dbs[c] += dy[c];
-        }
-        const float* in = y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2) * G1 + 2 * yy2) * G1 + 2 * z2) * C1 + ci;
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int tt = 0; tt < WG2_TT; ++tt) {
-            if (tt < ntap) {
-                float x = __ldg(in + off[tt]);
-                x = fmaxf(fmaf(a1, x, b1), 0.f);
+            for (int j = 0; j < 3; ++j)
+                bulk_g2s(dst + (uint32_t)((i * 3 + j) * LINE * 4),
+                         y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2 + i) * G1 + (2 * yy2 + j)) * G1) * C1, line_bytes, bar);
+        bulk_g2s(dst + (uint32_t)(9 * LINE * 4), dy2cl + ((int64_t)b * P2 + (int64_t)(x2 * G2 + yy2) * G2) * C1, dy_bytes, bar);
+    };
+    if (tid == 0 && r0 < r1) issue(r0, 0);
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    for (int row = r0; row < r1; ++row) {
+        const int stage = (row - r0) & 1;
+        if (tid == 0 && row + 1 < r1) issue(row + 1, stage ^ 1);     // stage^1 was released by the barrier ending row-1
+        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
+        phase[stage] ^= 1;
+        const float* lines = dsm + stage * STAGE;
+        const float* dyl = lines + 9 * LINE;
+        for (int z2 = g; z2 < G2; z2 += 4) {
+            const float4* dyp = reinterpret_cast<const float4*>(dyl + z2 * C1);
+            const float4 d0 = dyp[0], d1 = dyp[1], d2 = dyp[2], d3 = dyp[3];
+            const float dy[C1] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w, d2.x, d2.y, d2.z, d2.w, d3.x, d3.y, d3.z, d3.w};
+            if (t64 == 0) {
 #pragma unroll
-                for (int c = 0; c < C1; ++c) acc[tt][c] = fmaf(dy[c], x, acc[tt][c]);
+                for (int c = 0; c < C1; ++c) dbs[c] += dy[c];
+            }
+            const float* in = lines + 2 * z2 * C1;
+#pragma unroll
+            for (int tt = 0; tt < WG2_TT; ++tt) {
+                if (tt < ntap) {
+                    float x = in[off[tt]];
+                    x = fmaxf(fmaf(a1, x, b1), 0.f);
+#pragma unroll
+                    for (int c = 0; c < C1; ++c) acc[tt][c] = fmaf(dy[c], x, acc[tt][c]);
+                }
             }
         }
+        __syncthreads();                                    // everyone is done with this stage before it is refilled
     }
-    // cross-stream reduction in a fixed order: streams 1..3 publish, stream 0 adds them in order and writes the record
-    if (stream > 0) {
-        float* dst = sred + (stream - 1) * WG2_REC;
+    if (!ok) { asm volatile("trap;"); }
+    // cross-group reduction in a fixed order: groups 1..3 publish, group 0 adds them in order and writes the record
+    float* sred = dsm;
+    if (g > 0) {
+        float* dst = sred + (g - 1) * WG2_REC;
 #pragma unroll
         for (int tt = 0; tt < WG2_TT; ++tt)
             if (tt < ntap) {
@@ -455,7 +513,7 @@ conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1
         }
     }
     __syncthreads();
-    if (stream == 0) {
+    if (g == 0) {
         float* out = part + (int64_t)blockIdx.x * WG2_REC;
 #pragma unroll
         for (int tt = 0; tt < WG2_TT; ++tt)
@@ -508,6 +566,9 @@ conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w,
     __syncthreads();
     const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
     const int ZQ = ((G1 + 1) / 2 + DG2_ZT - 1) / DG2_ZT;
+    // Item order: parity class (x&1, y&1, z&1) is the SLOWEST index, so that the 32 threads of a warp (almost always)
+    // share one class and therefore one tap set -- the tap loops below are then warp-uniform.
+    const int NE = (G1 + 1) / 2, NO = G1 / 2;                 // number of even / odd coordinates
     const int items = G1 * G1 * 2 * ZQ;
     const int item = blockIdx.x * DG2_THREADS + tid;
     const bool active = item < items;
@@ -520,10 +581,17 @@ conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w,
 #pragma unroll
     for (int c = 0; c < C1; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
     if (active) {
-        int t = item;
+        // decode: classes ordered (xpar, ypar, zpar); inside a class: (x index, y index, zq)
+        int t = item, xpar = 0, ypar = 0, zpar = 0;
+        for (int cls = 0; cls < 8; ++cls) {
+            const int cx = (cls >> 2) & 1, cy = (cls >> 1) & 1, cz = cls & 1;
+            const int cnt = (cx ? NO : NE) * (cy ? NO : NE) * ZQ;
+            if (t < cnt) { xpar = cx; ypar = cy; zpar = cz; break; }
+            t -= cnt;
+        }
         const int zq = t % ZQ; t /= ZQ;
-        const int zpar = t & 1; t >>= 1;
-        const int yi = t % G1, xi = t / G1;
+        const int ny = ypar ? NO : NE;
+        const int yi = 2 * (t % ny) + ypar, xi = 2 * (t / ny) + xpar;
         const int zfirst = zpar + 2 * DG2_ZT * zq;                   // z of s = 0; z(s) = zfirst + 2s
         for (int i = 0; i < 3; ++i) {
             const int xr = xi - i;
@@ -824,8 +892,8 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.bmerge1 = 0;
     w.dz = w.dcat = w.dh1 = w.dact2 = w.dy2cl = w.g1 = w.bn2part = w.coef2 = w.bpart1 = w.coef1 = w.wg2part = w.wg1part = 0;
     w.nblk_dg = (int)ceil_div((int64_t)d.G1 * d.G1 * 2 * ceil_div((d.G1 + 1) / 2, DG2_ZT), DG2_THREADS);
-    w.wg2_pps = (int)std::max<int64_t>(16, ceil_div((int64_t)d.B * d.P2, (int64_t)WG2_MAX_BLOCKS * 4));
-    w.nblk_wg2 = (int)ceil_div((int64_t)d.B * d.P2, 4 * (int64_t)w.wg2_pps);
+    w.wg2_pps = (int)std::max<int64_t>(1, ceil_div((int64_t)d.B * d.G2 * d.G2, (int64_t)WG2_MAX_BLOCKS));   // rows per block
+    w.nblk_wg2 = (int)ceil_div((int64_t)d.B * d.G2 * d.G2, (int64_t)w.wg2_pps);
     w.wg1_items = (int64_t)d.B * d.G1 * d.G1 * ((d.G1 + 1) / 2);
     w.wg1_ips = (int)std::max<int64_t>(16, ceil_div(w.wg1_items, (int64_t)WG1_MAX_BLOCKS * (WG1_THREADS / 4)));
     w.nblk_wg1 = (int)ceil_div(w.wg1_items, (int64_t)(WG1_THREADS / 4) * w.wg1_ips);
@@ -1007,10 +1075,12 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     GNBV_LAUNCH_CHECK("bn2 backward");
     // ---- conv2 backward
     stage_mark(GNBV_ST_BWD_CONV2_WGRAD, stream);
-    const size_t smem_wg2 = 3 * (size_t)WG2_REC * 4;
+    const size_t line_f = (size_t)((d.G1 * C1 + 31) / 32) * 32, dyl_f = (size_t)((d.G2 * C1 + 31) / 32) * 32;
+    const size_t smem_wg2 = std::max(3 * (size_t)WG2_REC, 2 * (9 * line_f + dyl_f)) * 4;
+    GNBV_REQUIRE(smem_wg2 <= 200 * 1024, "gnbv_encoder_backward: grid too large for the conv2 wgrad staging buffers");
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
     conv2_wgrad_kernel<<<w.nblk_wg2, WG2_THREADS, smem_wg2, stream>>>(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, d.G1,
-                                                                       d.G2, (int64_t)B * d.P2, w.wg2_pps);
+                                                                       d.G2, B * d.G2 * d.G2, w.wg2_pps);
     GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);

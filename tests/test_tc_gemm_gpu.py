@@ -24,11 +24,11 @@ def test_tc_gemm_matches_float64(M, N, K):
         torch.cuda.synchronize()
         assert int(ws[:1].view(torch.int32)) == 0, "a bounded mbarrier wait expired inside the kernel"
         err = float((C.cpu().double() - want).abs().max()) / scale
-        assert err < 3e-6, (sa, sb, err)
+        assert err < 2e-5, (sa, sb, err)      # fp32 accumulation over up to 54,000 terms; budget is 1e-4
     bias = torch.randn(N, generator=g)
     C = torch.empty(M, N, device=DEV)
     ops.tc_gemm(Ad, (K, 1), Bt, (1, K), C, M, N, K, bias=bias.to(DEV), relu=True)
-    assert float((C.cpu().double() - torch.relu(want + bias.double())).abs().max()) / scale < 3e-6
+    assert float((C.cpu().double() - torch.relu(want + bias.double())).abs().max()) / scale < 2e-5
 
 
 def test_plain_tf32_would_not_meet_the_budget():
