@@ -788,6 +788,154 @@ conv1_wgrad_kernel(const float* __restrict__ obs, int64_t obs_stride, const int6
     }
 }
 
+// TMA-staged variant of conv1_wgrad_kernel (used when grid rows are 16 B aligned, i.e. G % 4 == 0).
+// Work unit = a block of up to 16 consecutive output rows (b, x1, y1 in [y0, y0+nr)): its input is three contiguous
+// slabs of the tri-class grid ((2 nr + 1) lines of G floats from planes 2x1, 2x1+1, 2x1+2) plus the contiguous g1 / y1
+// rows -- five bulk copies per stage, double-buffered against the FMA loop.  Thread mapping and accumulation order per
+// thread are those of conv1_wgrad_kernel (groups of 4 threads, z-pairs, 108 accumulators).
+constexpr int WG1_RB = 16;
+__global__ void __launch_bounds__(WG1_THREADS)
+conv1_wgrad_tma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
+                       const float* __restrict__ g1, const float* __restrict__ y1, const float* __restrict__ stat1,
+                       const float* __restrict__ coef, float* __restrict__ part, int G, int G1, int total_rb, int rb_per_block) {
+    extern __shared__ __align__(128) float dsm[];
+    __shared__ float red[WG1_THREADS / 32][WG1_REC];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int grp = tid >> 2, cg = tid & 3;
+    const int P1 = G1 * G1 * G1, M = (G1 + 1) / 2, NYB = (G1 + WG1_RB - 1) / WG1_RB;
+    const int TL = (2 * WG1_RB + 1) * G;                    // floats per staged tri slab
+    const int GL = WG1_RB * G1 * C1;                        // floats per staged g1 / y1 slab
+    const int STAGE = 3 * TL + 2 * GL;
+    float acc[TAPS][4];
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
+    float dbs[4] = {0.f, 0.f, 0.f, 0.f};
+    float a1[4], mean[4], invstd[4], k1[4], k2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = 4 * cg + q;
+        mean[q] = stat1[c]; invstd[q] = stat1[C1 + c]; a1[q] = stat1[2 * C1 + c]; k1[q] = coef[c]; k2[q] = coef[C1 + c];
+    }
+    const int rb0 = blockIdx.x * rb_per_block, rb1 = min(total_rb, rb0 + rb_per_block);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int rb, int& b, int& x1, int& y0, int& nr) {
+        b = rb / (G1 * NYB);
+        const int rem = rb - b * G1 * NYB;
+        x1 = rem / NYB;
+        y0 = (rem - x1 * NYB) * WG1_RB;
+        nr = min(WG1_RB, G1 - y0);
+    };
+    auto issue = [&](int rb, int stage) {                   // thread 0 only
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * STAGE);
+        const uint32_t tri_bytes = (uint32_t)(2 * nr + 1) * G * 4, g_bytes = (uint32_t)nr * G1 * C1 * 4;
+        mbar_expect_tx(bar, 3 * tri_bytes + 2 * g_bytes);
+        const float* orow = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            bulk_g2s(dst + (uint32_t)(i * TL * 4), orow + ((int64_t)(2 * x1 + i) * G + 2 * y0) * G, tri_bytes, bar);
+        const int64_t goff = ((int64_t)b * P1 + ((int64_t)x1 * G1 + y0) * G1) * C1;
+        bulk_g2s(dst + (uint32_t)(3 * TL * 4), g1 + goff, g_bytes, bar);
+        bulk_g2s(dst + (uint32_t)((3 * TL + GL) * 4), y1 + goff, g_bytes, bar);
+    };
+    if (tid == 0 && rb0 < rb1) issue(rb0, 0);
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    for (int rb = rb0; rb < rb1; ++rb) {
+        const int stage = (rb - rb0) & 1;
+        if (tid == 0 && rb + 1 < rb1) issue(rb + 1, stage ^ 1);
+        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
+        phase[stage] ^= 1;
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const float* ts = dsm + stage * STAGE;
+        const float* gs = ts + 3 * TL;
+        const float* ys = gs + GL;
+        for (int item = grp; item < nr * M; item += WG1_THREADS / 4) {
+            const int r = item / M, m = item - r * M, z1 = 2 * m;
+            const bool two = z1 + 1 < G1;
+            float dy[2][4];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) {
+                if (v == 0 || two) {
+                    const float4 gv = *reinterpret_cast<const float4*>(gs + ((r * G1 + z1 + v) * C1) + 4 * cg);
+                    const float4 yv = *reinterpret_cast<const float4*>(ys + ((r * G1 + z1 + v) * C1) + 4 * cg);
+                    const float g4[4] = {gv.x, gv.y, gv.z, gv.w}, y4[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        dy[v][q] = a1[q] * (g4[q] - k1[q] - ((y4[q] - mean[q]) * invstd[q]) * k2[q]);
+                        dbs[q] += dy[v][q];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) dy[v][q] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float* rp = ts + i * TL + (2 * r + j) * G + 2 * z1;
+                    const float4 v4 = *reinterpret_cast<const float4*>(rp);
+                    const float x4 = two ? rp[4] : 0.f;
+                    const float x[5] = {v4.x, v4.y, v4.z, v4.w, x4};
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        const int tap = (i * 3 + j) * 3 + l;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            acc[tap][q] = fmaf(dy[0][q], x[l], acc[tap][q]);
+                            acc[tap][q] = fmaf(dy[1][q], x[l + 2], acc[tap][q]);
+                        }
+                    }
+                }
+        }
+        __syncthreads();
+    }
+    if (!ok) { asm volatile("trap;"); }
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v = acc[t][q];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[t][q] = v;
+        }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float v = dbs[q];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        dbs[q] = v;
+    }
+    if (lane < 4) {
+#pragma unroll
+        for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[wid][(4 * cg + q) * TAPS + t] = acc[t][q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[wid][C1 * TAPS + 4 * cg + q] = dbs[q];
+    }
+    __syncthreads();
+    for (int j = tid; j < WG1_REC; j += WG1_THREADS) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < WG1_THREADS / 32; ++w) t += red[w][j];
+        part[(int64_t)blockIdx.x * WG1_REC + j] = t;
+    }
+}
+
 // ---- two-level reductions of the per-block statistics (keeps the final single-block kernels short) -----------------
 constexpr int MERGE_FAN = 64;
 // forward BN partials (mean, M2, count) -> one record per MERGE_FAN input records (same layout)
@@ -1098,6 +1246,21 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     // ---- conv1 backward (weights only: the input is data)
     stage_mark(GNBV_ST_BWD_CONV1_WGRAD, stream);
     const int vec1 = (d.G % 4 == 0) && (obs_row_stride % 4 == 0) && (state_dim % 4 == 0) && (((uintptr_t)obs & 15) == 0);
+    const size_t smem_wg1 = (size_t)2 * (3 * (2 * WG1_RB + 1) * d.G + 2 * WG1_RB * d.G1 * C1) * 4;
+    if (vec1 && smem_wg1 <= 190 * 1024) {
+        const int nyb = (int)ceil_div(d.G1, WG1_RB), total_rb = B * d.G1 * nyb;
+        const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, w.nblk_wg1));
+        const int nblk = (int)ceil_div(total_rb, rbpb);          // <= w.nblk_wg1: the partial buffer is large enough
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg1));
+        conv1_wgrad_tma_kernel<<<nblk, WG1_THREADS, smem_wg1, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1,
+                                                                        ws + w.stat1, ws + w.coef1, ws + w.wg1part, d.G, d.G1,
+                                                                        total_rb, rbpb);
+        GNBV_LAUNCH_CHECK("conv1_wgrad_tma_kernel");
+        reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, nblk, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
+        GNBV_LAUNCH_CHECK("reduce_records_kernel");
+        stage_mark(GNBV_ST_BWD_END, stream);
+        return GNBV_OK;
+    }
     conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
                                                                 ws + w.coef1, ws + w.wg1part, d.G, d.G1, w.wg1_items, w.wg1_ips, vec1);
     GNBV_LAUNCH_CHECK("conv1_wgrad_kernel");
