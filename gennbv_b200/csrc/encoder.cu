@@ -936,6 +936,112 @@ conv1_wgrad_tma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
     }
 }
 
+// TMA-staged conv1 forward (grid rows 16 B aligned).  Same work unit as conv1_wgrad_tma_kernel (row blocks of one x1
+// plane); one thread per z-quad: the four voxels share their nine 9-float input rows (2 LDS.128 + LDS.32 each), every
+// broadcast LDS.128 of weights feeds 16 FMA, each thread stores 256 contiguous bytes of the channels-last output.
+__global__ void __launch_bounds__(CONV1_THREADS)
+conv1_fwd_tma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
+                     const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y1,
+                     float* __restrict__ part, int G, int G1, int RBF, int total_rb, int rb_per_block) {
+    extern __shared__ __align__(128) float dsm[];
+    __shared__ __align__(16) float wsm[TAPS][C1];
+    __shared__ float bs[C1];
+    __shared__ float red[CONV1_THREADS / 32][PART_STRIDE];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < TAPS * C1; i += CONV1_THREADS) {
+        int tap = i / C1, c = i - tap * C1;
+        wsm[tap][c] = w[c * TAPS + tap];
+    }
+    if (tid < C1) bs[tid] = bias[tid];
+    const int P1 = G1 * G1 * G1, M = (G1 + 3) / 4, NYB = (G1 + RBF - 1) / RBF;      // M = z-quads per row
+    const int TL = (2 * RBF + 1) * G;
+    const int rb0 = blockIdx.x * rb_per_block, rb1 = min(total_rb, rb0 + rb_per_block);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int rb, int& b, int& x1, int& y0, int& nr) {
+        b = rb / (G1 * NYB);
+        const int rem = rb - b * G1 * NYB;
+        x1 = rem / NYB;
+        y0 = (rem - x1 * NYB) * RBF;
+        nr = min(RBF, G1 - y0);
+    };
+    auto issue = [&](int rb, int stage) {
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * 3 * TL);
+        const uint32_t tri_bytes = (uint32_t)(2 * nr + 1) * G * 4;
+        mbar_expect_tx(bar, 3 * tri_bytes);
+        const float* orow = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            bulk_g2s(dst + (uint32_t)(i * TL * 4), orow + ((int64_t)(2 * x1 + i) * G + 2 * y0) * G, tri_bytes, bar);
+    };
+    if (tid == 0 && rb0 < rb1) issue(rb0, 0);
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    for (int rb = rb0; rb < rb1; ++rb) {
+        const int stage = (rb - rb0) & 1;
+        if (tid == 0 && rb + 1 < rb1) issue(rb + 1, stage ^ 1);
+        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
+        phase[stage] ^= 1;
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const float* ts = dsm + stage * 3 * TL;
+        const bool active = tid < nr * M;
+        const int r = tid / M, q4 = tid - r * M, z1 = 4 * q4;
+        const int nv = active ? min(4, G1 - z1) : 0;                  // valid voxels of this thread's z-quad
+        float acc[4][C1];
+#pragma unroll
+        for (int sv = 0; sv < 4; ++sv)
+#pragma unroll
+            for (int c = 0; c < C1; ++c) acc[sv][c] = bs[c];
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float* rp = ts + i * TL + (2 * r + j) * G + 2 * z1;
+                    const float4 va = *reinterpret_cast<const float4*>(rp);
+                    const float4 vb = *reinterpret_cast<const float4*>(rp + 4);
+                    const float x[9] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w, rp[8]};
+#pragma unroll
+                    for (int l = 0; l < 3; ++l) {
+                        const float4* wr = reinterpret_cast<const float4*>(wsm[(i * 3 + j) * 3 + l]);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 wv = wr[q];
+#pragma unroll
+                            for (int sv = 0; sv < 4; ++sv) {
+                                const float xv = x[l + 2 * sv];
+                                acc[sv][4 * q + 0] = fmaf(xv, wv.x, acc[sv][4 * q + 0]);
+                                acc[sv][4 * q + 1] = fmaf(xv, wv.y, acc[sv][4 * q + 1]);
+                                acc[sv][4 * q + 2] = fmaf(xv, wv.z, acc[sv][4 * q + 2]);
+                                acc[sv][4 * q + 3] = fmaf(xv, wv.w, acc[sv][4 * q + 3]);
+                            }
+                        }
+                    }
+                }
+            float4* o = reinterpret_cast<float4*>(y1 + ((int64_t)b * P1 + ((int64_t)x1 * G1 + y0 + r) * G1 + z1) * C1);
+#pragma unroll
+            for (int sv = 0; sv < 4; ++sv)
+                if (sv < nv) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        o[4 * sv + q] = make_float4(acc[sv][4 * q], acc[sv][4 * q + 1], acc[sv][4 * q + 2], acc[sv][4 * q + 3]);
+                }
+        }
+        if (part) block_stats<CONV1_THREADS, 4>(acc, nv, part + (int64_t)rb * PART_STRIDE, red);
+        __syncthreads();
+    }
+    if (!ok) { asm volatile("trap;"); }
+}
+
 // ---- two-level reductions of the per-block statistics (keeps the final single-block kernels short) -----------------
 constexpr int MERGE_FAN = 64;
 // forward BN partials (mean, M2, count) -> one record per MERGE_FAN input records (same layout)
@@ -987,7 +1093,7 @@ namespace {
 
 struct EncDims {
     int B, G, G1, G2, P1, P2, S, FEAT, HID;
-    int nblk1, nblk2, items2;
+    int nblk1, nblk2, items2, rbf1, nrb1, nrec1;
     int64_t flat2;
 };
 
@@ -998,7 +1104,10 @@ EncDims make_dims(int B, int G, int state_dim) {
     d.G2 = (d.G1 - 3) / 2 + 1;
     d.P1 = d.G1 * d.G1 * d.G1; d.P2 = d.G2 * d.G2 * d.G2;
     d.S = state_dim; d.FEAT = 256; d.HID = 256;
+    d.rbf1 = std::max(1, std::min(d.G1, CONV1_THREADS / ((d.G1 + 3) / 4)));
+    d.nrb1 = d.G1 * (int)ceil_div(d.G1, d.rbf1);                    // row blocks per sample of the TMA-staged conv1 kernels
     d.nblk1 = (int)ceil_div(d.P1, CONV1_THREADS);
+    d.nrec1 = std::max(d.nblk1, d.nrb1);
     d.items2 = d.G2 * d.G2 * (int)ceil_div(d.G2, CONV2_ZT);
     d.nblk2 = (int)ceil_div(d.items2, CONV2_THREADS);
     d.flat2 = (int64_t)C1 * d.P2;
@@ -1024,12 +1133,12 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.h1 = take(B * d.HID);
     w.cat = take(B * 2 * d.HID);
     w.y1 = take(B * (size_t)d.P1 * C1);
-    w.part1 = take(B * (size_t)d.nblk1 * PART_STRIDE);
+    w.part1 = take(B * (size_t)d.nrec1 * PART_STRIDE);
     w.stat1 = take(4 * C1);
     w.y2 = take(B * (size_t)d.flat2);
     w.part2 = take(B * (size_t)d.nblk2 * PART_STRIDE);
     w.stat2 = take(4 * C1);
-    w.merge1 = take((size_t)ceil_div(B * (size_t)d.nblk1, MERGE_FAN) * PART_STRIDE);
+    w.merge1 = take((size_t)ceil_div(B * (size_t)d.nrec1, MERGE_FAN) * PART_STRIDE);
     w.merge2 = take((size_t)ceil_div(B * (size_t)d.nblk2, MERGE_FAN) * PART_STRIDE);
     w.act2 = take(B * (size_t)d.flat2);
     size_t g = 0;
@@ -1118,13 +1227,26 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     // ---- grid branch
     stage_mark(GNBV_ST_FWD_CONV1, stream);
     float* part1 = training ? ws + w.part1 : nullptr;
-    conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
-                                                                      ws + w.y1, part1, d.G, d.G1);
+    const int vec1f = (d.G % 4 == 0) && (obs_row_stride % 4 == 0) && (state_dim % 4 == 0) && (((uintptr_t)obs & 15) == 0);
+    const size_t smem_c1 = ((size_t)2 * 3 * (2 * d.rbf1 + 1) * d.G + 32) * 4;      // + pad: the last quad reads one float past its row
+    int nrec1;
+    if (vec1f && smem_c1 <= 160 * 1024) {
+        const int total_rb = B * d.nrb1;
+        const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, 1184));
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c1));
+        conv1_fwd_tma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), CONV1_THREADS, smem_c1, stream>>>(
+            obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
+        nrec1 = total_rb;
+    } else {
+        conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
+                                                                          ws + w.y1, part1, d.G, d.G1);
+        nrec1 = B * d.nblk1;
+    }
     GNBV_LAUNCH_CHECK("conv1_fwd_kernel");
     stage_mark(GNBV_ST_FWD_BN1, stream);
     if (training) {
-        const int nm = (int)ceil_div((int64_t)B * d.nblk1, MERGE_FAN);
-        bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part1, B * d.nblk1, ws + w.merge1);
+        const int nm = (int)ceil_div((int64_t)nrec1, MERGE_FAN);
+        bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part1, nrec1, ws + w.merge1);
         bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.merge1, nm, p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, p->bn1_nbt,
                                                       ws + w.stat1, 1e-5f, 0.1f);
     }
