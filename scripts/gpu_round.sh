@@ -18,7 +18,7 @@ if [ -z "$SKIP_NCU" ]; then
       --log-file $OUT/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $OUT/ncu_launch_bench.log 2>&1
   echo "== ncu full"
   timeout 1200 ncu --nvtx --nvtx-include "timed/" --set full --clock-control none --import-source on \
-      -k regex:'grid_update_kernel|scan_raycast_kernel|conv2_fwd_kernel|conv2_wgrad_kernel|conv2_dgrad_kernel|conv1_wgrad_kernel|conv1_fwd_kernel' \
+      -k regex:'grid_update_kernel|scan_raycast_kernel|conv2_fwd_kernel|conv2_wgrad_kernel|conv2_dgrad_kernel|conv1_wgrad_tma_kernel|conv1_fwd_tma_kernel' \
       -c 14 -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_bench.log 2>&1
 fi
 ls -la $OUT
