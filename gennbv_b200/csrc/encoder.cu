@@ -14,6 +14,9 @@
 //   * Linear layers use the fp32 split-K GEMM of gemm.cu (fp32 everywhere: the 1e-4 parity budget rules out
 //     bf16 / tf32 operands, see gemm.cuh).
 #include "gemm.cuh"
+#include "conv2_tc.cuh"
+
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -1093,7 +1096,7 @@ namespace {
 
 struct EncDims {
     int B, G, G1, G2, P1, P2, S, FEAT, HID;
-    int nblk1, nblk2, items2, rbf1, nrb1, nrec1;
+    int nblk1, nblk2, items2, rbf1, nrb1, nrec1, nrec2;
     int64_t flat2;
 };
 
@@ -1111,6 +1114,7 @@ EncDims make_dims(int B, int G, int state_dim) {
     d.items2 = d.G2 * d.G2 * (int)ceil_div(d.G2, CONV2_ZT);
     d.nblk2 = (int)ceil_div(d.items2, CONV2_THREADS);
     d.flat2 = (int64_t)C1 * d.P2;
+    d.nrec2 = std::max(d.nblk2, conv2_tc_supported(d.G1, d.G2) ? conv2_tc_tiles(1, d.G2) : 0);
     return d;
 }
 
@@ -1136,10 +1140,10 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.part1 = take(B * (size_t)d.nrec1 * PART_STRIDE);
     w.stat1 = take(4 * C1);
     w.y2 = take(B * (size_t)d.flat2);
-    w.part2 = take(B * (size_t)d.nblk2 * PART_STRIDE);
+    w.part2 = take(B * (size_t)d.nrec2 * PART_STRIDE);
     w.stat2 = take(4 * C1);
     w.merge1 = take((size_t)ceil_div(B * (size_t)d.nrec1, MERGE_FAN) * PART_STRIDE);
-    w.merge2 = take((size_t)ceil_div(B * (size_t)d.nblk2, MERGE_FAN) * PART_STRIDE);
+    w.merge2 = take((size_t)ceil_div(B * (size_t)d.nrec2, MERGE_FAN) * PART_STRIDE);
     w.act2 = take(B * (size_t)d.flat2);
     size_t g = 0;
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, 4 * d.S));
@@ -1255,13 +1259,23 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     GNBV_LAUNCH_CHECK("bn1 statistics");
     stage_mark(GNBV_ST_FWD_CONV2, stream);
     float* part2 = training ? ws + w.part2 : nullptr;
-    conv2_fwd_kernel<<<dim3(d.nblk2, B), CONV2_THREADS, 0, stream>>>(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2,
-                                                                      part2, d.G1, d.G2);
+    // conv2 on the tcgen05 tensor cores (3xTF32 implicit GEMM, conv2_tc.cu) unless GNBV_CONV2_TC=0 or the grid is unsupported
+    static const bool use_tc = []() { const char* e = getenv("GNBV_CONV2_TC"); return !(e && e[0] == '0'); }();
+    int nrec2;
+    if (use_tc && conv2_tc_supported(d.G1, d.G2)) {
+        rc = launch_conv2_fwd_tc(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2, part2, nullptr, B, d.G1, d.G2, stream);
+        if (rc) return rc;
+        nrec2 = conv2_tc_tiles(B, d.G2);
+    } else {
+        conv2_fwd_kernel<<<dim3(d.nblk2, B), CONV2_THREADS, 0, stream>>>(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2,
+                                                                          part2, d.G1, d.G2);
+        nrec2 = B * d.nblk2;
+    }
     GNBV_LAUNCH_CHECK("conv2_fwd_kernel");
     stage_mark(GNBV_ST_FWD_BN2, stream);
     if (training) {
-        const int nm = (int)ceil_div((int64_t)B * d.nblk2, MERGE_FAN);
-        bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part2, B * d.nblk2, ws + w.merge2);
+        const int nm = (int)ceil_div((int64_t)nrec2, MERGE_FAN);
+        bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part2, nrec2, ws + w.merge2);
         bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.merge2, nm, p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, p->bn2_nbt,
                                                       ws + w.stat2, 1e-5f, 0.1f);
     }

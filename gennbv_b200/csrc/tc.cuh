@@ -85,14 +85,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // ---- descriptors + MMA ---------------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version = 1 [46,48), base_offset 0, layout_type SWIZZLE_NONE = 0 [61,64)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
-    d |= (uint64_t)((LBO_BYTES >> 4) & 0x3fff) << 16;
-    d |= (uint64_t)((SBO_BYTES >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
     d |= (uint64_t)1 << 46;
     return d;
 }
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) { return make_smem_desc(smem_addr, LBO_BYTES, SBO_BYTES); }
 
 // instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B
 __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
