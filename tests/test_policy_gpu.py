@@ -221,3 +221,28 @@ def test_clip_and_adam_match_torch():
         assert abs(float(ws[0]) / float(norm) - 1) < 1e-4      # torch sums 1.1 M squares in fp32; the kernel in double
         # parameters are O(1) and the update O(1e-4): compare at fp32 resolution of the parameters (<= 2 ulp of 4.0)
         assert float((p.cpu() - p_ref.detach()).abs().max()) <= 1e-6
+
+
+def test_tcgen05_conv2_path_is_parity_green():
+    """The opt-in tensor-core conv2 forward (GNBV_CONV2_TC=1, 3xTF32 implicit GEMM) reproduces the fp32 reference."""
+    import subprocess, sys, os
+    code = (
+        "import sys, os; sys.path[:0] = [%r, %r, %r]\n"
+        "import torch, encoder_ref\n"
+        "from test_policy_gpu import make_policy, rel_err\n"
+        "for G, B in ((64, 3), (20, 9)):\n"
+        "    pol, ref, D = make_policy(G, 1)\n"
+        "    g = torch.Generator().manual_seed(0)\n"
+        "    obs = torch.zeros(B, D); obs[:, :600] = torch.randn(B, 600, generator=g)\n"
+        "    obs[:, 600:600 + G ** 3] = torch.randint(-1, 2, (B, G ** 3), generator=g).float()\n"
+        "    for tr in (False, True):\n"
+        "        ref.train(tr); pol.train(tr)\n"
+        "        with torch.no_grad():\n"
+        "            e = rel_err(pol.features_extractor(obs.cuda()).cpu(), ref.features_extractor(obs))\n"
+        "        assert e < 1e-4, (G, tr, e)\n"
+        "print('tc-conv2 ok')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                     os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
+                                     os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "GNBV_CONV2_TC": "1"}, capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0 and "tc-conv2 ok" in out.stdout, out.stdout + out.stderr
