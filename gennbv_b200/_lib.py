@@ -75,6 +75,8 @@ SIGNATURES = {
     "gnbv_tc_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gnbv_tc_gemm": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
                              c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "gnbv_chamfer_workspace_bytes": (c_size_t, [c_int]),
+    "gnbv_chamfer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnbv_gae": (c_int, [c_void_p] * 5 + [c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

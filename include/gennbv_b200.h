@@ -284,6 +284,15 @@ int gnbv_tc_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int
                  int64_t ldc, int M, int N, int K, const float* bias, int relu, float* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* ---- eval accuracy ("next" row): exact bidirectional 1-NN / chamfer ----
+ * Replaces pytorch3d.loss.chamfer_distance as called by gennbv/env/env_eval_gennbv.py:253-261 (pytorch3d is a third-party
+ * dependency, "0.7.8 works" per the reference README, not vendored; defaults: squared L2, mean over points, both
+ * directions).  Clouds are packed: x [sum P1_e, 3] f32 with offsets [E+1] i64, same for y.
+ *   cham_x[e] = mean_i min_j |x_i - y_j|^2,  cham_y[e] = mean_j min_i |x_i - y_j|^2;  the loss is their sum. */
+size_t gnbv_chamfer_workspace_bytes(int num_clouds);
+int gnbv_chamfer(const float* x, const int64_t* x_offsets, const float* y, const int64_t* y_offsets, int num_clouds,
+                 float* cham_x, float* cham_y, float* workspace, size_t workspace_bytes, void* stream);
+
 /* TensorRolloutBuffer_Grid_Obs.compute_returns_and_advantage  (stable_baselines3/common/buffers.py:706-724)
  *   rewards, values [T,N] f32; episode_starts [T,N] u8; last_values [N] f32; dones [N] u8
  *   advantages, returns [T,N] f32 out.  gamma / gae_lambda are the Python doubles of the buffer. */
