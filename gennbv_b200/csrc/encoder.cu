@@ -210,6 +210,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 // ------------------------------------------------------------------------------------------------ conv2
 // Conv3d(16,16,3,stride 2) as an implicit GEMM; input y1 [B,G1^3,16] with BN1 affine + ReLU applied on load,
 // output y2 [B,16,G2^3] (pre-BN, channel-major = the order nn.Flatten feeds the grid Linear).
+// (forcing 4 resident blocks/SM via launch bounds spills and measured no gain: the kernel is LSU/FMA co-bound, not occupancy-bound)
 __global__ void __launch_bounds__(CONV2_THREADS)
 conv2_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ w,
                  const float* __restrict__ bias, float* __restrict__ y2, float* __restrict__ part, int G1, int G2) {

@@ -157,7 +157,15 @@ class ActorCriticPolicy_Train_Eval(nn.Module):
     def forward(self, obs, deterministic=False):
         """policies.py:999-1015 -> actions [N,6] i64, values [N,1], log_prob [N]."""
         with torch.no_grad():
-            feats = self.extract_features(obs)
+            return self.act_from_features(self.extract_features(obs), deterministic)
+
+    def values_from_features(self, feats):
+        """value_net on already-extracted features (rollout-time reuse of one encoder pass per step)."""
+        with torch.no_grad():
+            return self._heads(feats)[:, self.num_logits:]
+
+    def act_from_features(self, feats, deterministic=False):
+        with torch.no_grad():
             out = self._heads(feats)
             B, A = out.shape[0], self.num_logits
             actions = torch.empty(B, len(self.nvec), dtype=torch.int64, device=out.device)

@@ -103,20 +103,28 @@ class PPO_Grid_Obs:
         self.policy.set_training_mode(False)
         buf.reset()
         n_steps = 0
+        # One encoder pass per env step instead of the reference's two: in eval mode with fixed weights
+        # predict_values(new_obs) at step t and policy(obs) at step t+1 see the same observation,
+        # so the features extracted for the bootstrap are reused for the next action.  Results are identical.
+        with torch.no_grad():
+            feats = self.policy.extract_features(self._last_obs)
         while n_steps < n_rollout_steps:
-            actions, values, log_probs = self.policy(self._last_obs)
+            actions, values, log_probs = self.policy.act_from_features(feats)
             new_obs, rewards, dones, infos = env.step(actions)
             self.num_timesteps += env.num_envs
             if callback is not None and callback(locals()) is False:
                 return False
             self.ep_info_buffer.append(infos.get("episode"))
             n_steps += 1
+            with torch.no_grad():
+                feats = self.policy.extract_features(new_obs)
+            new_values = self.policy.values_from_features(feats)
             # time-out bootstrap (:205-208); `[0]` picks env 0's value for every env -- reproduced, not fixed
-            terminal_value = self.policy.predict_values(new_obs)[0]
+            terminal_value = new_values[0]
             rewards += self.gamma * torch.squeeze(terminal_value * infos["time_outs"].unsqueeze(1).to(self.device), 1)
             buf.add(self._last_obs, actions, rewards, self._last_episode_starts, values, log_probs)
             self._last_obs, self._last_episode_starts = new_obs, dones
-        values = self.policy.predict_values(new_obs)
+        values = new_values                                   # == policy.predict_values(new_obs) (:213-215)
         buf.compute_returns_and_advantage(last_values=values, dones=dones)
         return True
 
@@ -172,6 +180,19 @@ class PPO_Grid_Obs:
                                         self._current_progress_remaining)), 0.9, 0.999,
                                     float(pol.optimizer_kwargs.get("eps", 1e-8)), self._adam_step, grad_scale, s),
                    "gnbv_adam_step")
+
+    def sync_optimizer_state(self):
+        """Mirror the fused Adam state (flat exp_avg / exp_avg_sq arenas, step count) into `policy.optimizer.state`, so
+        that `policy.optimizer.state_dict()` -- what SB3's save() pickles as policy.optimizer.pth
+        (on_policy_algorithm_grid_obs.py:300-303) -- reflects the training done by the fused path."""
+        pol = self.policy
+        order = pol.features_extractor._param_list() + [pol.action_net.weight, pol.value_net.weight, pol.action_net.bias,
+                                                        pol.value_net.bias]
+        for p, (o, n) in zip(order, pol._arena):
+            st = pol.optimizer.state[p]
+            st["step"] = torch.tensor(float(self._adam_step))
+            st["exp_avg"] = self._exp_avg[o:o + n].view_as(p)
+            st["exp_avg_sq"] = self._exp_avg_sq[o:o + n].view_as(p)
 
     def _mb_ws(self, B):
         if getattr(self, "_mb", None) is None or self._mb["feats"].shape[0] != B:
