@@ -10,6 +10,11 @@
 // CTA.  One thread issues 18 tcgen05.mma.kind::tf32 per stage; two A stages + tcgen05.commit -> mbarrier overlap the
 // loads of stage s+1 with the MMAs of stage s.  Epilogue: tcgen05.ld -> + bias -> channel-major store + Welford
 // statistics for BatchNorm2 (one record per tile).
+// Status: parity-green but opt-in (GNBV_CONV2_TC=1): measured 1.43 ms vs 0.55 ms for the CUDA-core kernel at B = 256, because
+// each staged A element feeds only N = 16 MACs while its staging costs ~20 instructions.  Design note for a follow-up: a
+// space-to-depth shared-memory layout [x-plane][y parity][z parity][ci quad][y/2][z/2] x 16 B makes the A tile of every tap a
+// plain UMMA descriptor view (SBO = 128 B between 8-voxel groups, LBO = one ci-quad block), so each activation is
+// transformed and stored once instead of 3.4 times (M = 64 tiles of 4 rows x 16 voxels fit 178 KB of shared memory).
 #include "conv2_tc.cuh"
 #include "tc.cuh"
 
