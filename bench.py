@@ -372,6 +372,9 @@ def run_native(args, rank, world):
 
 
 def main():
+    if os.environ.get("GNBV_BENCH_FAULT_DUMP"):          # debugging aid: dump all Python stacks if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["GNBV_BENCH_FAULT_DUMP"]), exit=False)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
