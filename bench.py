@@ -204,7 +204,9 @@ def run_native(args, rank, world):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # bounded collectives: a wedged peer makes the run fail after 3 minutes instead of hanging the box
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     N, V, P = ENVS_PER_GPU, G ** 3, H * W
     wl = make_workload(N, dev, seed=rank)
     K, Wm = args.steps, args.warmup
