@@ -164,7 +164,7 @@ reset_envs_kernel(uint8_t* __restrict__ reset_buf, float* __restrict__ prob, flo
                   float* __restrict__ pose_hist, float* __restrict__ rgb_hist, float* __restrict__ ratio_prev,
                   int64_t* __restrict__ actions, int64_t* __restrict__ episode_length, float* __restrict__ episode_sums,
                   const float* __restrict__ init_pose, const int64_t* __restrict__ init_action, int N, int V, int BA,
-                  int A, int KF, int vec_ok, int clear_flag) {
+                  int A, int KF, int vec_ok) {
     const int n = blockIdx.y;
     if (!reset_buf[n]) return;
     const size_t base = (size_t)n * V;
@@ -182,9 +182,8 @@ reset_envs_kernel(uint8_t* __restrict__ reset_buf, float* __restrict__ prob, flo
     if (gtid < A) actions[n * A + gtid] = init_action[gtid];
     if (gtid < 3) episode_sums[gtid * N + n] = 0.0f;
     if (gtid == 0) { ratio_prev[n] = 0.0f; episode_length[n] = 0; }
-    // reset_buf[env_ids] = 0 after the step (env_train_gennbv.py:373) is applied by the caller-visible flag copy:
-    // `dones_out` keeps the done flags; the last block to finish clears reset_buf only if asked to
-    (void)clear_flag;
+    // reset_buf[env_ids] = 0 (env_train_gennbv.py:373) is applied afterwards by clear_flags_kernel: `dones_out` of
+    // gnbv_reward_termination keeps the done flags for the caller
 }
 
 __global__ void clear_flags_kernel(uint8_t* flags, int N) {
@@ -269,7 +268,7 @@ extern "C" int gnbv_reset_envs(uint8_t* reset_buf, float* prob_grid, float* scan
     dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(V, 1024 * 4), 64)), (unsigned)N);
     reset_envs_kernel<<<grid, 256, 0, stream>>>(reset_buf, prob_grid, scanned_gt, pose_hist, rgb_hist, ratio_prev, actions,
                                                 episode_length, episode_sums, init_pose, init_action, N, (int)V,
-                                                hist_len * pose_dim, pose_dim, rgb_frames * rgb_h * rgb_w, vec_ok, 0);
+                                                hist_len * pose_dim, pose_dim, rgb_frames * rgb_h * rgb_w, vec_ok);
     GNBV_LAUNCH_CHECK("reset_envs_kernel");
     if (clear_reset_buf) {
         clear_flags_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(reset_buf, N);

@@ -26,8 +26,6 @@ from .config import Config_GenNBV_Train
 from .sensors import SensorFrame, SensorSource
 from .spaces import Box, Dict, MultiDiscrete
 
-_c = _lib
-
 
 def _dptr(t):
     return None if t is None else t.data_ptr()

@@ -170,7 +170,6 @@ class PPO_Grid_Obs:
         torch.sum(w["dout"], dim=0, out=pol.head_b_grad)
         enc._run_backward(buf.flat("observations"), w["feats"], w["dfeat"], B, True, ws, row_index=rows, grads=self._enc_grads)
         n = pol.flat_grads.numel()
-        grad_scale = 1.0
         gdist.allreduce_mean_(pol.flat_grads)                        # NCCL over NVLink, one flat bucket, before the clip
         _lib.check(L.gnbv_grad_norm(pol.flat_grads.data_ptr(), n, float(self.max_grad_norm), self._clip_ws.data_ptr(), s),
                    "gnbv_grad_norm")
@@ -178,7 +177,7 @@ class PPO_Grid_Obs:
         _lib.check(L.gnbv_adam_step(pol.flat_params.data_ptr(), pol.flat_grads.data_ptr(), self._exp_avg.data_ptr(),
                                     self._exp_avg_sq.data_ptr(), n, self._clip_ws.data_ptr(), float(self.lr_schedule(
                                         self._current_progress_remaining)), 0.9, 0.999,
-                                    float(pol.optimizer_kwargs.get("eps", 1e-8)), self._adam_step, grad_scale, s),
+                                    float(pol.optimizer_kwargs.get("eps", 1e-8)), self._adam_step, 1.0, s),
                    "gnbv_adam_step")
 
     def sync_optimizer_state(self):
