@@ -559,10 +559,12 @@ constexpr int DG2_THREADS = 128;
 constexpr int DG2_ZT = 4;
 __global__ void __launch_bounds__(DG2_THREADS)
 conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w, const float* __restrict__ y1,
-                   const float* __restrict__ stat1, float* __restrict__ g1, float* __restrict__ bpart, int G1, int G2) {
+                   const float* __restrict__ stat1, float* __restrict__ g1, float* __restrict__ bpart, int G1, int G2,
+                   int vblocks_per_sample, int total_vblocks) {
     __shared__ __align__(16) float ws[TAPS][C1][C1];        // [tap][co][ci]
     __shared__ float red[DG2_THREADS / 32][2 * C1];
-    const int tid = threadIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x;
+    // persistent block: the 27 KB weight tile is staged once, then the block walks virtual blocks (sample, item chunk)
     for (int i = tid; i < TAPS * C1 * C1; i += DG2_THREADS) {
         int tap = i / (C1 * C1), r = i - tap * C1 * C1, co = r / C1, ci = r - co * C1;
         ws[tap][co][ci] = w[(co * C1 + ci) * TAPS + tap];
@@ -574,7 +576,9 @@ conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w,
     // share one class and therefore one tap set -- the tap loops below are then warp-uniform.
     const int NE = (G1 + 1) / 2, NO = G1 / 2;                 // number of even / odd coordinates
     const int items = G1 * G1 * 2 * ZQ;
-    const int item = blockIdx.x * DG2_THREADS + tid;
+    for (int vb = blockIdx.x; vb < total_vblocks; vb += gridDim.x) {
+    const int b = vb / vblocks_per_sample, vblk = vb - b * vblocks_per_sample;
+    const int item = vblk * DG2_THREADS + tid;
     const bool active = item < items;
     float acc[DG2_ZT][C1];
 #pragma unroll
@@ -673,7 +677,9 @@ conv2_dgrad_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w,
         float t = 0.f;
 #pragma unroll
         for (int wv = 0; wv < DG2_THREADS / 32; ++wv) t += red[wv][tid];
-        bpart[((int64_t)b * gridDim.x + blockIdx.x) * 2 * C1 + tid] = t;
+        bpart[(int64_t)vb * 2 * C1 + tid] = t;
+    }
+    __syncthreads();                                          // red[] is reused by the next virtual block
     }
 }
 
@@ -1372,8 +1378,9 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);
     stage_mark(GNBV_ST_BWD_CONV2_DGRAD, stream);
-    conv2_dgrad_kernel<<<dim3(w.nblk_dg, B), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1,
-                                                                        ws + w.bpart1, d.G1, d.G2);
+    conv2_dgrad_kernel<<<std::min(B * w.nblk_dg, 148 * 3), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1,
+                                                                                      ws + w.g1, ws + w.bpart1, d.G1, d.G2, w.nblk_dg,
+                                                                                      B * w.nblk_dg);
     GNBV_LAUNCH_CHECK("conv2_dgrad_kernel");
     stage_mark(GNBV_ST_BWD_BN1, stream);
     {
