@@ -51,7 +51,7 @@ SIGNATURES = {
     "gnbv_obs_update": (c_int, [c_void_p] * 5 + [c_int64] * 3 + [c_int] * 8 + [c_void_p]),
     "gnbv_episode_stats_doubles": (c_size_t, []),
     "gnbv_reward_termination": (c_int, [c_void_p] * 14 + [c_double] * 3 + [c_int] * 3 + [c_int64, c_double, c_double,
-                                                                                       c_int, c_void_p]),
+                                                                                       c_int, c_int, c_void_p]),
     "gnbv_reset_envs": (c_int, [c_void_p] * 11 + [c_int] * 8 + [c_void_p]),
     "gnbv_encoder_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "gnbv_encoder_forward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
@@ -77,6 +77,12 @@ SIGNATURES = {
                              c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "gnbv_chamfer_workspace_bytes": (c_size_t, [c_int]),
     "gnbv_chamfer": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnbv_chamfer_grid_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int]),
+    "gnbv_chamfer_grid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnbv_nn_sqdist_brute": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnbv_scan_points": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int64, c_uint32, c_void_p]),
+    "gnbv_keys_to_points": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "gnbv_gae": (c_int, [c_void_p] * 5 + [c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

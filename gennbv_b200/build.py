@@ -18,6 +18,7 @@ PER_FILE = {
     "voxelize.cu": ["-fmad=false"],
     "gae.cu": ["-fmad=false"],
     "env_step.cu": ["-fmad=false"],
+    "eval_points.cu": ["-fmad=false"],
 }
 
 

@@ -49,3 +49,15 @@ class Config_GenNBV_Train:
 
     class control:
         decimation = 4                            # dt = decimation * sim_params.dt  (drone_robot.py:874-875)
+
+
+class Config_GenNBV_Eval(Config_GenNBV_Train):
+    """gennbv/env/config_gennbv_eval.py:6-15.  `rewards` is redefined, not extended: only the coverage term remains
+    (scale 50 x dt 0.02 = 1, "just easy to evaluate") and negative totals are clipped."""
+    max_episode_length = 30
+
+    class rewards:
+        class scales:
+            surface_coverage = 50
+        only_positive_rewards = True
+        max_contact_force = 100.

@@ -75,6 +75,7 @@ obs_update_kernel(const uchar4* __restrict__ rgba, const float* __restrict__ pos
 struct RewardParams {
     float scale_cov, scale_short, scale_term;   // reward_scales[...] (already x dt), cast to fp32 like torch does
     int has_term, only_positive, max_step_done;
+    int accumulate_reset;                       // eval env: `reset_buf |= ...` (env_eval_gennbv.py:327-333) instead of `=`
     int64_t max_episode_length;
     float max_episode_length_s;
     float ratio_threshold;
@@ -111,7 +112,7 @@ reward_termination_kernel(const float* __restrict__ cov_sum, const float* __rest
         // check_termination (:438-457)
         bool col = collision ? collision[n] != 0 : false;
         bool tout = p.max_step_done ? (len >= p.max_episode_length) : (time_out_buf[n] != 0);
-        bool rst = col || (p.max_step_done && tout) || (ratio > p.ratio_threshold);
+        bool rst = col || (p.max_step_done && tout) || (ratio > p.ratio_threshold) || (p.accumulate_reset && reset_buf[n] != 0);
         if (p.has_term) {                                                  // _reward_termination (:555-556)
             float r_term = __fmul_rn((rst && !tout) ? 1.0f : 0.0f, p.scale_term);
             rew = __fadd_rn(rew, r_term);
@@ -236,7 +237,7 @@ extern "C" int gnbv_reward_termination(const float* cov_sum, const float* num_va
                                        uint8_t* time_outs_extra, double scale_cov, double scale_short, double scale_term,
                                        int has_termination_reward, int only_positive_rewards, int max_step_done,
                                        int64_t max_episode_length, double max_episode_length_s, double ratio_threshold,
-                                       int N, void* stream) {
+                                       int accumulate_reset, int N, void* stream) {
     GNBV_REQUIRE(cov_sum && num_valid && ratio_prev && episode_length && rew_buf && reset_buf && time_out_buf && dones_out &&
                      episode_sums && cur_reward_sum && cur_episode_length && stats && time_outs_extra,
                  "gnbv_reward_termination: null pointer argument");
@@ -246,6 +247,7 @@ extern "C" int gnbv_reward_termination(const float* cov_sum, const float* num_va
     p.has_term = has_termination_reward; p.only_positive = only_positive_rewards; p.max_step_done = max_step_done;
     p.max_episode_length = max_episode_length; p.max_episode_length_s = (float)max_episode_length_s;
     p.ratio_threshold = (float)ratio_threshold;
+    p.accumulate_reset = accumulate_reset;
     reward_termination_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(cov_sum, num_valid, ratio_prev, episode_length, collision,
                                                                     rew_buf, reset_buf, time_out_buf, dones_out, episode_sums,
                                                                     cur_reward_sum, cur_episode_length, stats,

@@ -88,7 +88,8 @@ class Env_Train_GenNBV:
         self.pose_hist = self._init_pose.repeat(N, self.buffer_size, 1).contiguous()     # oldest first
         self.k, self.rgb_h, self.rgb_w = 2, 64, 64
         self.rgb_hist = torch.zeros(N, self.k, self.rgb_h, self.rgb_w, device=dev)
-        self.ratio_threshold_term = 0.99
+        self.ratio_threshold_term = 0.99                   # check_termination (env_train_gennbv.py:454-457)
+        self._accumulate_reset = False                     # `reset_buf = ...` here, `|=` in the eval env
         self._ratio = torch.zeros(N, device=dev)
         self.reward_ratio_buf = _RatioHistory(self._ratio)
         self.cur_reward_sum = torch.zeros(N, device=dev)
@@ -241,6 +242,13 @@ class Env_Train_GenNBV:
         c2w[:, :3, 3] -= self.env_origins
         return c2w.contiguous().to(self.device, non_blocking=True)
 
+    # hooks of the eval env (gennbv_b200/env_eval.py); no-ops here
+    def _after_occ_grid_update(self, frame, c2w):
+        pass
+
+    def _before_reset_idx(self):
+        pass
+
     def post_physics_step(self, if_reset=False):
         """env_train_gennbv.py:328-375 (post_physics_step + get_step_return) as 6 launches."""
         L, s, N, G = _lib.lib(), ops._stream(), self.num_envs, self.grid_size
@@ -270,6 +278,7 @@ class Env_Train_GenNBV:
                         self._cov_sum, self._workspace, tri_row_stride=self.obs_dim)
         if ev is not None:
             ev[2].record()
+        self._after_occ_grid_update(frame, c2w)
         # compute_reward / check_termination / episode statistics
         rs = self.reward_scales
         _lib.check(L.gnbv_reward_termination(
@@ -281,8 +290,9 @@ class Env_Train_GenNBV:
             float(rs.get("surface_coverage", 0.0)), float(rs.get("short_path", 0.0)), float(rs.get("termination", 0.0)),
             int("termination" in rs), int(bool(self.cfg.rewards.only_positive_rewards)),
             int(bool(self.cfg.termination.max_step_done)), int(self.max_episode_length), float(self.max_episode_length_s),
-            float(self.ratio_threshold_term), N, s), "gnbv_reward_termination")
+            float(self.ratio_threshold_term), int(self._accumulate_reset), N, s), "gnbv_reward_termination")
         obs = self._obs_dict()
+        self._before_reset_idx()
         # reset_idx for the done envs (the returned observation is the pre-reset one, as in the reference)
         self._reset_flagged(clear=True)
         st = self._stats

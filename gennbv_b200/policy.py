@@ -191,8 +191,11 @@ class ActorCriticPolicy_Train_Eval(nn.Module):
         with torch.no_grad():
             return self._heads(self.extract_features(obs))[:, self.num_logits:]
 
-    def predict(self, obs, deterministic=True):
-        return self.forward(obs, deterministic=deterministic)[0]
+    def predict(self, observation, state=None, episode_start=None, deterministic=False):
+        """policies.py:425-477 -> (actions, state).  Eval mode; actions stay on the device as an int64 tensor (the
+        reference converts them to numpy and the eval env converts them straight back, env_eval_gennbv.py:138-141)."""
+        self.set_training_mode(False)
+        return self.forward(observation, deterministic=deterministic)[0], state
 
 
 class _NoCtx:

@@ -244,6 +244,10 @@ class PPO_Grid_Obs:
             rec("train/clip_range_vf", clip_range_vf)
         rec("time/training", time.time() - t0)
 
+    def predict(self, observation, state=None, episode_start=None, deterministic=False):
+        """base_class_grid_obs.py:578-598."""
+        return self.policy.predict(observation, state, episode_start, deterministic)
+
     def learn(self, total_timesteps, callback=None, log_interval=1, **unused):
         """on_policy_algorithm_grid_obs.py:230-298."""
         self._setup_learn()

@@ -108,6 +108,24 @@ def make_house_scenes(num_scenes: int, G: int, seed: int = 0) -> HouseScenes:
     return HouseScenes(params=params, grid_gt=grid)
 
 
+def gt_point_clouds(params: torch.Tensor, num_envs: int, num_points: int, seed: int = 0):
+    """Per-env GT surface clouds (list of [num_points,3] float32), the stand-in for the reference's
+    data_gennbv/eval/gt/point_cloud/BAT12_SETA_HOUSE{e+1}_pc.pt files (env_eval_gennbv.py:93-101): a seeded random subset
+    of dense samples on the visible faces of scene e % S."""
+    g = torch.Generator().manual_seed(seed)
+    S = params.shape[0]
+    out = []
+    for e in range(num_envs):
+        lx, ly, hw, hr = (float(v) for v in params[e % S])
+        area = 2 * lx * hw + 2 * ly * (hw + hr / 2) + 2 * lx * math.hypot(ly / 2, hr)
+        dense = _surface_samples(lx, ly, hw, hr, max(math.sqrt(area / (4.0 * num_points)), 1e-3))
+        while dense.shape[0] < num_points:
+            dense = torch.cat([dense, dense + 1e-4], 0)
+        sel = torch.randperm(dense.shape[0], generator=g)[:num_points]
+        out.append(dense[sel].float().contiguous())
+    return out
+
+
 def gt_metadata(grid_gt: torch.Tensor):
     """voxel_size_gt [S,3], num_valid_voxel_gt [S], range_gt [S,6] -- the derivations of
     `Env_Train_GenNBV._init_load_all` (env_train_gennbv.py:66-80), same fp32 arithmetic."""

@@ -1,4 +1,4 @@
-"""`EnvWrapperGenNBVTrain` -- flattens the observation dict to [N, D] (gennbv/wrapper/env_wrapper_gennbv_train.py).
+"""`EnvWrapperGenNBVTrain` / `EnvWrapperGenNBVEval` -- flatten the observation dict to [N, D] (gennbv/wrapper/env_wrapper_gennbv_train.py).
 
 The reference concatenates `state | grid | state_rgb` into a new tensor every step (:27-56, one full copy of the
 observation).  `gennbv_b200.Env_Train_GenNBV` already keeps its observation in that layout, so the wrapper returns
@@ -47,3 +47,15 @@ class EnvWrapperGenNBVTrain:
 
     def close(self):
         self._gym_env.close()
+
+
+class EnvWrapperGenNBVEval(EnvWrapperGenNBVTrain):
+    """gennbv/wrapper/env_wrapper_gennbv_eval.py:87-140: same flattening, five-element returns (accuracy dict last)."""
+
+    def reset(self):
+        obs, rews, dones, infos, accs = self._gym_env.reset()
+        return self._flatten_observation(obs), rews, dones, infos, accs
+
+    def step(self, action):
+        obs, reward, done, info, accs = self._gym_env.step(action)
+        return self._flatten_observation(obs), reward, done, info, accs

@@ -157,14 +157,16 @@ size_t gnbv_episode_stats_doubles(void);
  * (env_train_base.py:629-639) and reset_idx's episode statistics (env_train_gennbv.py:424-436).
  * All [N]; flags are u8 {0,1}; episode_sums [3,N] (coverage, short_path, termination); scales are the Python
  * doubles reward_scales[name] (cfg scale x dt). collision may be NULL (no contacts).
- * time_outs_extra reproduces infos["time_outs"], which the reference rebinds only inside reset_idx. */
+ * time_outs_extra reproduces infos["time_outs"], which the reference rebinds only inside reset_idx.
+ * ratio_threshold: coverage-ratio termination (0.99 in the train env, +inf = none as in the eval env);
+ * accumulate_reset != 0: the eval env's `reset_buf |= ...` (env_eval_gennbv.py:327-333) -- flags already set stay set. */
 int gnbv_reward_termination(const float* cov_sum, const float* num_valid, float* ratio_prev, int64_t* episode_length,
                             const uint8_t* collision, float* rew_buf, uint8_t* reset_buf, uint8_t* time_out_buf,
                             uint8_t* dones_out, float* episode_sums, float* cur_reward_sum, float* cur_episode_length,
                             double* stats, uint8_t* time_outs_extra, double scale_cov, double scale_short,
                             double scale_term, int has_termination_reward, int only_positive_rewards, int max_step_done,
                             int64_t max_episode_length, double max_episode_length_s, double ratio_threshold,
-                            int num_envs, void* stream);
+                            int accumulate_reset, int num_envs, void* stream);
 
 /* reset_idx's buffer resets for rows with reset_buf != 0 (env_train_gennbv.py:395-421): grids zeroed, pose history
  * <- init_pose, frames <- 0, ratio <- 0, actions <- init_action, episode_length <- 0, episode_sums <- 0;
@@ -292,6 +294,19 @@ int gnbv_tc_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int
 size_t gnbv_chamfer_workspace_bytes(int num_clouds);
 int gnbv_chamfer(const float* x, const int64_t* x_offsets, const float* y, const int64_t* y_offsets, int num_clouds,
                  float* cham_x, float* cham_y, float* workspace, size_t workspace_bytes, void* stream);
+/* Same result through an exact uniform-grid nearest-neighbour search (per direction: bounding box, per-cell counts,
+ * exclusive scan, counting-sort fill, shell search -- gennbv_b200/csrc/nn_grid.cuh) instead of the P1*P2 scan.
+ *   total_x / total_y = x_offsets[E] / y_offsets[E] (known to the host; they size the workspace);
+ *   cells_per_axis in [1,160]: cells along the longest bounding-box axis of every cloud (cubic cells);
+ *   min_x [total_x] / min_y [total_y] f32: optional per-point minima (NULL to skip); equal to the brute-force kernel's
+ *   bit for bit.  The workspace must be 256-byte aligned. */
+size_t gnbv_chamfer_grid_workspace_bytes(int num_clouds, int64_t total_x, int64_t total_y, int cells_per_axis);
+int gnbv_chamfer_grid(const float* x, const int64_t* x_offsets, const float* y, const int64_t* y_offsets, int num_clouds,
+                      int64_t total_x, int64_t total_y, int cells_per_axis, float* cham_x, float* cham_y,
+                      float* min_x, float* min_y, void* workspace, size_t workspace_bytes, void* stream);
+/* Per-point minima min_j |q_i - r_j|^2 of the brute-force scan (cross-check entry; workspace as gnbv_chamfer). */
+int gnbv_nn_sqdist_brute(const float* q, const int64_t* q_offsets, const float* r, const int64_t* r_offsets, int num_clouds,
+                         float* min_out, float* workspace, size_t workspace_bytes, void* stream);
 
 /* TensorRolloutBuffer_Grid_Obs.compute_returns_and_advantage  (stable_baselines3/common/buffers.py:706-724)
  *   rewards, values [T,N] f32; episode_starts [T,N] u8; last_values [N] f32; dones [N] u8
@@ -299,6 +314,18 @@ int gnbv_chamfer(const float* x, const int64_t* x_offsets, const float* y, const
 int gnbv_gae(const float* rewards, const float* values, const uint8_t* episode_starts,
              const float* last_values, const uint8_t* dones, double gamma, double gae_lambda,
              int n_steps, int num_envs, float* advantages, float* returns, void* stream);
+
+/* ---- eval env: scanned-point history (gennbv/env/env_eval_gennbv.py:160-164, 253-257) ----
+ * gnbv_scan_points: back_projection_fg (env_train_gennbv.py:494-526) for every foreground pixel (seg > 50), same fp32
+ * chain as the voxelize path, appended to env n's history as the packed 1 cm lattice key
+ *   key = (kx + 2^20) << 42 | (ky + 2^20) << 21 | (kz + 2^20),  k = nearbyint(p * 100.f)   (== torch.round(p, decimals=2) * 100)
+ * keys [N, capacity] i64, counts [N] i32 in/out (number of keys held), overflow [1] i32 set to 1 if a history is full.
+ * Ascending key order is the row order of torch.unique(dim=0) on the rounded points.  flags: GNBV_RAW_DEPTH as above.
+ * gnbv_keys_to_points: keys [n] -> points [n,3] f32 = k / 100.f, the rows torch.round(decimals=2) produces. */
+int gnbv_scan_points(const float* depth, const int32_t* seg, const float* kinv, const float* c2w, int64_t* keys,
+                     int32_t* counts, int32_t* overflow, int num_envs, int height, int width, int64_t capacity,
+                     uint32_t flags, void* stream);
+int gnbv_keys_to_points(const int64_t* keys, int64_t num_keys, float* points, void* stream);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,77 @@ def main():
 
 
 
+def eval_rollout(name, N, H, W, G, S, T, max_episode_length, seed, n_gt, reset_at=()):
+    """Roll-out of the reference's unmodified `Env_Eval_GenNBV` on CPU (pytorch3d's chamfer_distance replaced by the float64
+    restatement in ref_driver, everything else the reference's own lines).  Records, besides the train fixture's inputs,
+    the five-element returns, the per-env point-history sizes after every call and -- whenever the env computes an
+    accuracy -- the deduplicated 1 cm cloud it handed to chamfer_distance."""
+    torch.manual_seed(seed)
+    scenes = synth.make_house_scenes(S, G, seed=seed)
+    pc_gt = synth.gt_point_clouds(scenes.params, N, n_gt, seed=seed)
+    env, ref = ref_driver.make_reference_env(N, H, W, scenes, buffer_size=100, max_episode_length=max_episode_length,
+                                             eval_env=True, pc_gt=pc_gt)
+    env_eval_mod = sys.modules["gennbv.env.env_eval_gennbv"]
+    gen = torch.Generator().manual_seed(seed + 1)
+    keys = ("depth", "seg", "rgb", "view", "tri", "ratio", "rew", "done", "ep_len", "hist_sizes", "acc", "is_reset")
+    rec = {k: [] for k in keys}
+    clouds = []                                              # (call index, dedup cloud) in the order chamfer is called
+    inner = env_eval_mod.chamfer_distance
+
+    def chamfer_spy(x, y):
+        clouds.append((len(rec["rew"]), x[0].numpy().copy()))
+        return inner(x, y)
+
+    env_eval_mod.chamfer_distance = chamfer_spy
+
+    def snap(out, is_reset):
+        obs, rew, done, info, acc = out
+        rec["depth"].append(torch.stack(env.depth_cam_tensors).numpy().copy())
+        rec["seg"].append(torch.stack(env.seg_cam_tensors).numpy().copy())
+        rec["rgb"].append(torch.stack(env.rgb_cam_tensors).numpy().copy())
+        rec["view"].append(env._view_matrix.copy())
+        rec["tri"].append(obs["grid"].numpy().astype(np.int8))
+        rec["ratio"].append(env.reward_ratio_buf[-1].numpy().copy())
+        rec["rew"].append(rew.numpy().copy())
+        rec["done"].append(done.numpy().copy())
+        rec["ep_len"].append(env.episode_length_buf.numpy().copy())
+        rec["hist_sizes"].append(np.array([p.shape[0] for p in env.pts_target_list], np.int64))
+        rec["acc"].append(np.array([acc.get(str(e), np.nan) for e in range(N)], np.float64))
+        rec["is_reset"].append(np.array(is_reset))
+
+    snap(env.reset(), True)
+    actions = []
+    for t in range(T):
+        if t in reset_at:
+            snap(env.reset(), True)
+            actions.append(np.zeros((N, 6), np.int64))
+            continue
+        a = synth.sample_lookat_actions(scenes.params, N, gen)
+        actions.append(a.numpy().copy())
+        snap(env.step(a), False)
+    out = {k: np.stack(v) for k, v in rec.items()}
+    out["actions"] = np.stack(actions)
+    out["cloud_call"] = np.array([c for c, _ in clouds], np.int64)
+    out["cloud_sizes"] = np.array([p.shape[0] for _, p in clouds], np.int64)
+    out["cloud_points"] = np.concatenate([p for _, p in clouds], 0) if clouds else np.zeros((0, 3), np.float32)
+    out["pc_gt"] = np.stack([p.numpy() for p in pc_gt])
+    out["range_gt"] = env.range_gt.numpy()
+    out["voxel_size_gt"] = env.voxel_size_gt.numpy()
+    out["num_valid_voxel_gt"] = env.num_valid_voxel_gt.numpy()
+    out["env_origins"] = env.env_origins.numpy()
+    out["inv_intri"] = env.inv_intri.numpy()
+    out["reward_scale_cov"] = np.array(env.reward_scales["surface_coverage"], np.float64)
+    out["grid_gt_file"] = np.packbits(scenes.grid_gt[..., 3].numpy().astype(bool), axis=None)
+    out["grid_centres_lohi"] = np.stack([scenes.grid_gt[:, 0, 0, 0, :3].numpy(), scenes.grid_gt[:, -1, -1, -1, :3].numpy()], 1)
+    out["scene_params"] = scenes.params.numpy()
+    out["meta"] = np.array([N, H, W, G, S, T, max_episode_length, seed], np.int64)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    env_eval_mod.chamfer_distance = inner
+    print(f"{path}: {os.path.getsize(path) / 1e6:.2f} MB; dones={int(out['done'].sum())} chamfer calls={len(clouds)} "
+          f"cloud sizes={out['cloud_sizes'].tolist()} acc(last)={out['acc'][-1]}")
+
+
 # ------------------------------------------------------------------------------------------------ policy goldens
 def policy_golden(name="policy_g20", seed=7):
     """Outputs of the reference's own Hybrid_Encoder / ActorCriticPolicy_Train_Eval / PPO loss lines at the
@@ -198,6 +269,10 @@ def policy_golden(name="policy_g20", seed=7):
 
 
 if __name__ == "__main__":
+    if "--eval" in sys.argv:
+        # two 4-step episodes, a reset() in the middle of the third (accuracy of partial histories), then more steps
+        eval_rollout("env_eval_g20", N=3, H=40, W=40, G=20, S=2, T=13, max_episode_length=4, seed=11, n_gt=1500, reset_at=(10,))
+        sys.exit(0)
     if "--policy" not in sys.argv:
         main()
     policy_golden()

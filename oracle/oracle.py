@@ -108,3 +108,31 @@ def gae(rewards, values, episode_starts, last_values, dones, gamma=0.99, lam=0.9
     lib().gnbv_oracle_gae(_p(rewards), _p(values), _p(es), _p(lv), _p(dn), ctypes.c_double(gamma),
                           ctypes.c_double(lam), T, N, _p(adv), _p(ret))
     return adv, ret
+
+
+# ---- eval accuracy (gennbv/env/env_eval_gennbv.py:250-264) ------------------------------------------------------------
+def round_1cm_unique(points):
+    """`torch.unique(torch.round(pts, decimals=2), dim=0)` (:254-257).  torch.round(decimals=2) is
+    nearbyint(x * 100.f) / 100.f in fp32 (ATen round_decimals_kernel); unique(dim=0) returns the distinct rows in
+    lexicographic order."""
+    p = _c(points, np.float32).reshape(-1, 3)
+    r = (np.rint(p * np.float32(100.0)) / np.float32(100.0)).astype(np.float32)
+    return np.unique(r, axis=0) if r.shape[0] else r
+
+
+def chamfer(x, y):
+    """pytorch3d.loss.chamfer_distance with the defaults used at env_eval_gennbv.py:258 (third party, 0.7.x, not vendored in
+    the reference -- its published definition: squared L2, mean over points, both directions summed), for one cloud pair,
+    via an exact float64 k-d tree.  Returns (mean_x min_y d^2, mean_y min_x d^2)."""
+    from scipy.spatial import cKDTree
+    x, y = np.asarray(x, np.float64).reshape(-1, 3), np.asarray(y, np.float64).reshape(-1, 3)
+    dx, _ = cKDTree(y).query(x, k=1)
+    dy, _ = cKDTree(x).query(y, k=1)
+    return float(np.mean(dx ** 2)), float(np.mean(dy ** 2))
+
+
+def nn_sqdist(q, r):
+    """Exact min_j |q_i - r_j|^2 in float64 (k-d tree), [P] -- checker for the per-point minima of the CUDA search."""
+    from scipy.spatial import cKDTree
+    d, _ = cKDTree(np.asarray(r, np.float64)).query(np.asarray(q, np.float64), k=1)
+    return d ** 2

@@ -46,19 +46,38 @@ def _bresenham_cpu(pts_source, pts_target, map_size):
     return torch.from_numpy(out).to(torch.long)
 
 
-def make_reference_env(num_envs, H, W, scenes, buffer_size=100, max_episode_length=100, with_rgb=True):
-    """-> (env, ref) where env is a CPU instance of the reference's Env_Train_GenNBV."""
+def chamfer_distance_restated(x, y):
+    """Stand-in for pytorch3d.loss.chamfer_distance (third party, "0.7.8 works" per the reference README, not vendored,
+    absent here) with its defaults as called at env_eval_gennbv.py:258: squared L2, point_reduction="mean",
+    batch_reduction="mean", both directions summed; float64 brute force.  Returns (loss, None) like pytorch3d."""
+    d = torch.cdist(x.double(), y.double()) ** 2                 # [B,P1,P2]
+    loss = d.min(2).values.mean(1) + d.min(1).values.mean(1)     # [B]
+    return loss.mean().float(), None
+
+
+def make_reference_env(num_envs, H, W, scenes, buffer_size=100, max_episode_length=100, with_rgb=True, eval_env=False,
+                       pc_gt=None):
+    """-> (env, ref) where env is a CPU instance of the reference's Env_Train_GenNBV (or, with eval_env=True, of its
+    Env_Eval_GenNBV with `pc_gt` = list of per-env GT clouds and pytorch3d's chamfer replaced by the restatement above)."""
     ref = ref_loader.load_reference()
     ref.env_train.bresenham3D_pycuda = _bresenham_cpu
-    Env = ref.env_train.Env_Train_GenNBV
-    from gennbv.env.config_gennbv_train import Config_GenNBV_Train
+    if eval_env:
+        env_eval_mod = __import__("gennbv.env.env_eval_gennbv", fromlist=["x"])
+        env_eval_mod.bresenham3D_pycuda = _bresenham_cpu
+        env_eval_mod.chamfer_distance = chamfer_distance_restated
+        Env = env_eval_mod.Env_Eval_GenNBV
+        from gennbv.env.config_gennbv_eval import Config_GenNBV_Eval as Config
+    else:
+        Env = ref.env_train.Env_Train_GenNBV
+        from gennbv.env.config_gennbv_train import Config_GenNBV_Train as Config
 
-    cfg = Config_GenNBV_Train()
+    cfg = Config()
     cfg.max_episode_length = max_episode_length
     cfg.visual_input.stack = buffer_size
     cfg.visual_input.camera_height, cfg.visual_input.camera_width = H, W
     cfg.env.num_envs = num_envs
-    cfg.rewards.only_positive_rewards = False     # train_gennbv.py:101-106 overrides the config (SURVEY section 5)
+    if not eval_env:
+        cfg.rewards.only_positive_rewards = False     # train_gennbv.py:101-106 overrides the config (SURVEY section 5)
     cfg.return_visual_observation = True
     if cfg.terrain.mesh_type not in ["heightfield", "trimesh"]:     # drone_robot.py:879-880
         cfg.terrain.curriculum = False
@@ -87,8 +106,16 @@ def make_reference_env(num_envs, H, W, scenes, buffer_size=100, max_episode_leng
     env.env_origins[:, 0] = cfg.env.env_spacing * xx.flatten()[:num_envs]
     env.env_origins[:, 1] = cfg.env.env_spacing * yy.flatten()[:num_envs]
     # GT: run the reference's _init_load_all on the synthetic file content
-    with patch.object(torch, "load", lambda *a, **k: scenes.grid_gt.clone()):
+    def fake_load(path, *a, **k):
+        name = os.path.basename(str(path))
+        if name.endswith("_pc.pt"):                              # BAT12_SETA_HOUSE{env+1}_pc.pt (env_eval_gennbv.py:95-101)
+            return pc_gt[int("".join(ch for ch in name.split("HOUSE")[1] if ch.isdigit())) - 1].clone()
+        return scenes.grid_gt.clone()
+
+    with patch.object(torch, "load", fake_load):
         env._init_load_all()
+    if eval_env:
+        env.ratios_accuracy = dict()                             # Env_Eval_GenNBV._init_buffers (:103-105)
     # the part of _init_buffers that does not touch Isaac Gym (env_train_gennbv.py:123-202)
     env.contact_forces = torch.zeros(num_envs, 6, 3)
     env.termination_contact_indices = torch.tensor([0, 2, 3, 4, 5])
