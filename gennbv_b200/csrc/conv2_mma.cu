@@ -1,0 +1,465 @@
+// conv2_mma.cu -- Conv3d(16,16,3,stride 2) forward of the Hybrid_Encoder (hybrid_encoder.py:35-37) as an implicit GEMM on
+// the tensor cores through warp-level mma.sync (m16n8k8, TF32 operands, fp32 accumulation) with split-precision (3xTF32)
+// operands: x = x_hi + x_lo, w = w_hi + w_lo, acc += x_lo*w_hi + x_hi*w_lo + x_hi*w_hi.  The dropped lo*lo term is
+// ~2^-22 relative, i.e. fp32-level, which keeps the <= 1e-4 parity budget with the reference's fp32 (TF32-off) cuDNN path
+// that plain TF32 operands would not (tests/test_tc_gemm_gpu.py::test_plain_tf32_would_not_meet_the_budget).
+//
+// Why mma.sync here and not tcgen05 (conv2_tc.cu): with N = 16 output channels each activation feeds only 16 MACs, and
+// the activation needs BN1 + ReLU + the hi/lo split on its way in.  UMMA wants its A operand in a canonical shared-memory
+// layout, so every activation was loaded, transformed, split and re-stored (~20 instructions per element, measured 1.43 ms
+// vs 0.55 ms for the CUDA-core kernel).  mma.sync takes A from REGISTERS: a thread loads the 4 consecutive channels it
+// owns as one 128-bit load, applies BN + ReLU + split in place and issues the MMAs -- no im2col copy at all.
+//
+// Mapping.  GEMM rows = output voxels, K = 27 taps x 16 input channels, N = 16.  A warp owns MT = 4 row tiles of 16
+// voxels.  Within a tap the 16 input channels are two k-steps of 8; the k order inside a k-step is permuted so that
+// thread t (= lane & 3) supplies channels 4t..4t+3: k-step A uses (4t, 4t+1) for the fragment's k slots (t, t+4), k-step B
+// uses (4t+2, 4t+3).  The weight fragments follow the same permutation and sit pre-split (hi / lo) in shared memory in
+// exactly the order the threads read them: [tap][ntile*2 + part][lane] as float4 -> conflict-free LDS.128.
+#include "common.cuh"
+#include "conv2_mma.cuh"
+
+#include <algorithm>
+
+namespace gnbv {
+
+namespace {
+
+constexpr int C = 16;
+constexpr int NTAPS = 27;
+constexpr int MMA_THREADS = 128;
+constexpr int MMA_WARPS = MMA_THREADS / 32;
+constexpr int MT = 4;                               // m16 tiles per warp
+constexpr int ROWS_PER_WARP = 16 * MT;              // 64 output voxels
+constexpr int ROWS_PER_ITEM = ROWS_PER_WARP * MMA_WARPS;   // 256 output voxels per work item
+constexpr int WSM_FLOAT4 = NTAPS * 4 * 32;          // 3456 float4 = 55,296 B
+constexpr int MMA_PART_STRIDE = 2 * C + 4;          // == PART_STRIDE of encoder.cu: mean[16], M2[16], count, pad
+constexpr size_t MMA_SMEM = (size_t)WSM_FLOAT4 * 16 + (size_t)(2 * MMA_WARPS * C + C) * 4;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+struct Split4 { uint32_t hi[4], lo[4]; };
+
+// relu(a * y + b) for the thread's 4 channels, split into tf32 hi / lo.
+// `cvt.rna.tf32.f32` is not a native instruction on sm_100a (ptxas expands it to ~4 instructions with an infinity check), so
+// the split is spelled out: hi = round-to-nearest of the 13 dropped mantissa bits (add half an ulp, mask); lo = v - hi is
+// exact in fp32 and is handed over as is -- the tensor core reads only its upper 19 bits, an error below 2^-21 |v|.
+// (Activations are finite and far from FLT_MAX, the only place where the unchecked add could overflow.)
+__device__ __forceinline__ Split4 bn_relu_split(float4 y, const float (&sc)[4], const float (&sh)[4]) {
+    const float v[4] = {fmaxf(fmaf(sc[0], y.x, sh[0]), 0.f), fmaxf(fmaf(sc[1], y.y, sh[1]), 0.f),
+                        fmaxf(fmaf(sc[2], y.z, sh[2]), 0.f), fmaxf(fmaf(sc[3], y.w, sh[3]), 0.f)};
+    Split4 s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s.hi[k] = (__float_as_uint(v[k]) + 0x1000u) & 0xffffe000u;
+        s.lo[k] = __float_as_uint(v[k] - __uint_as_float(s.hi[k]));
+    }
+    return s;
+}
+
+__device__ __forceinline__ Split4 split4(float4 y) {
+    const float v[4] = {y.x, y.y, y.z, y.w};
+    Split4 s;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s.hi[k] = (__float_as_uint(v[k]) + 0x1000u) & 0xffffe000u;
+        s.lo[k] = __float_as_uint(v[k] - __uint_as_float(s.hi[k]));
+    }
+    return s;
+}
+
+// y1 [B, G1^3, 16] channels-last (pre-BN conv1 output); stat1[2*16 + c] = BN1 scale, stat1[3*16 + c] = BN1 shift;
+// w [16,16,3,3,3]; y2 [B,16,G2^3] channel-major pre-BN (bias added); part: one (mean[16], M2[16], count) record per item.
+__global__ void __launch_bounds__(MMA_THREADS, 3)
+conv2_fwd_mma_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ w,
+                     const float* __restrict__ bias, float* __restrict__ y2, float* __restrict__ part, int G1, int G2,
+                     int chunks, int items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* wsm = reinterpret_cast<float4*>(smem_raw);                       // [tap][q][lane]
+    float* red = reinterpret_cast<float*>(smem_raw + (size_t)WSM_FLOAT4 * 16);   // [2][warps][16] partial sums
+    float* bmean = red + 2 * MMA_WARPS * C;                                  // [16]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+    // ---- stage the weight fragments, pre-split, in the order the threads consume them
+    for (int idx = tid; idx < WSM_FLOAT4; idx += MMA_THREADS) {
+        const int tap = idx >> 7, q = (idx >> 5) & 3, ln = idx & 31;
+        const int gg = ln >> 2, tt = ln & 3, j = q >> 1, lo_part = q & 1;
+        const int co = 8 * j + gg;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float wv = __ldg(w + ((int64_t)co * C + (4 * tt + e)) * NTAPS + tap);
+            const float hi = __uint_as_float(to_tf32(wv));
+            v[e] = lo_part ? __uint_as_float(to_tf32(wv - hi)) : hi;
+        }
+        wsm[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    float sc[4], sh[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { sc[e] = stat1[2 * C + 4 * t + e]; sh[e] = stat1[3 * C + 4 * t + e]; }
+    float bias_r[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) bias_r[j][e] = bias[8 * j + 2 * t + e];
+    __syncthreads();
+
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / chunks, chunk = item - b * chunks;
+        const int row0 = chunk * ROWS_PER_ITEM + warp * ROWS_PER_WARP;
+        const float* in_b = y1 + (int64_t)b * P1 * C + 4 * t;
+        // input offsets (floats) of the thread's rows g and g+8 of every m-tile; rows past P2 alias the last voxel
+        int off[MT][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = min(row0 + m * 16 + g + 8 * h, P2 - 1);
+                const int z2 = p % G2, r = p / G2, yy2 = r % G2, x2 = r / G2;
+                off[m][h] = (((2 * x2) * G1 + 2 * yy2) * G1 + 2 * z2) * C;
+            }
+        float acc[MT][2][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { acc[m][j][0] = acc[m][j][2] = bias_r[j][0]; acc[m][j][1] = acc[m][j][3] = bias_r[j][1]; }
+
+        for (int ij = 0; ij < 9; ++ij) {
+            const int i = ij / 3, jy = ij - 3 * i;
+            const int tap_off = ((i * G1 + jy) * G1) * C;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) {
+                const int tap = ij * 3 + l;
+                const float4* wt = wsm + tap * 128 + lane;
+                const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];       // ntile 0 hi/lo, ntile 1 hi/lo
+                const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
+                                           {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
+                const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
+                                           {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
+                float4 raw[MT][2];
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        raw[m][h] = __ldg(reinterpret_cast<const float4*>(in_b + off[m][h] + tap_off + l * C));
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    const Split4 r0 = bn_relu_split(raw[m][0], sc, sh), r1 = bn_relu_split(raw[m][1], sc, sh);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {             // k-step A: channels (4t, 4t+1); k-step B: (4t+2, 4t+3)
+                        const int e0 = 2 * ks, e1 = 2 * ks + 1;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
+                            mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
+                            mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- store y2 (channel-major) and the block's BN statistics record
+        const int nrows_item = min(ROWS_PER_ITEM, P2 - chunk * ROWS_PER_ITEM);   // > 0 by construction of `chunks`
+        float s[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int p = row0 + m * 16 + g + 8 * h;
+                if (p < P2) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float v = acc[m][j][2 * h + e];
+                            y2[((int64_t)b * C + (8 * j + 2 * t + e)) * P2 + p] = v;
+                            s[j][e] += v;
+                        }
+                }
+            }
+        if (part) {                                    // uniform branch
+            // pass 1: block mean per channel
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float v = s[j][e];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (g == 0) red[warp * C + 8 * j + 2 * t + e] = v;
+                }
+            __syncthreads();
+            if (tid < C) {
+                float tot = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < MMA_WARPS; ++wv) tot += red[wv * C + tid];
+                bmean[tid] = tot / (float)nrows_item;
+            }
+            __syncthreads();
+            // pass 2: centred sum of squares
+            float q2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    if (row0 + m * 16 + g + 8 * h < P2) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const float dlt = acc[m][j][2 * h + e] - bmean[8 * j + 2 * t + e];
+                                q2[j][e] = fmaf(dlt, dlt, q2[j][e]);
+                            }
+                    }
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float v = q2[j][e];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    if (g == 0) red[(MMA_WARPS + warp) * C + 8 * j + 2 * t + e] = v;
+                }
+            __syncthreads();
+            if (tid < C) {
+                float m2 = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < MMA_WARPS; ++wv) m2 += red[(MMA_WARPS + wv) * C + tid];
+                float* pr = part + (int64_t)item * MMA_PART_STRIDE;
+                pr[tid] = bmean[tid];
+                pr[C + tid] = m2;
+                if (tid == 0) pr[2 * C] = (float)nrows_item;
+            }
+            __syncthreads();                           // red / bmean are reused by the next item
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// conv2 data gradient + ReLU / BN1-backward statistics (same contract as conv2_dgrad_kernel in encoder.cu):
+//   dact1[b,v,ci] = sum_{taps with (v - tap) even and in range} sum_co dy2[b,(v - tap)/2,co] * W2[co,ci,tap]
+//   g1 = dact1 * [bn1(y1) > 0]  (channels-last);  bpart[item][0..16) = sum g1, [16..32) = sum g1 * xhat1.
+// The 8 parity classes (x&1, y&1, z&1) of the conv1-output grid each have a fixed tap set (2 or 1 taps per axis), so a
+// work item = 256 voxels of ONE class of one sample is a dense GEMM: rows = voxels, K = (taps of the class) x 16 co, N = 16 ci.
+// A rows are contiguous 16-channel dy2 vectors (one LDG.128 per thread and row, zeros outside the output grid), split
+// hi/lo in registers; B = W2[tap][co][ci] fragments pre-split in shared memory like the forward kernel's.
+struct DgradClass { int cx, cy, cz, nx, ny, nz, nvox, chunks; };
+
+__device__ __host__ inline DgradClass dgrad_class(int cls, int G1) {
+    const int NE = (G1 + 1) / 2, NO = G1 / 2;
+    DgradClass c;
+    c.cx = (cls >> 2) & 1; c.cy = (cls >> 1) & 1; c.cz = cls & 1;
+    c.nx = c.cx ? NO : NE; c.ny = c.cy ? NO : NE; c.nz = c.cz ? NO : NE;
+    c.nvox = c.nx * c.ny * c.nz;
+    c.chunks = (c.nvox + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM;
+    return c;
+}
+
+__global__ void __launch_bounds__(MMA_THREADS, 3)
+conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict__ w, const float* __restrict__ y1,
+                       const float* __restrict__ stat1, float* __restrict__ g1, float* __restrict__ bpart, int G1, int G2,
+                       int items_per_sample, int total_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* wsm = reinterpret_cast<float4*>(smem_raw);                           // [tap][q][lane]
+    float* red = reinterpret_cast<float*>(smem_raw + (size_t)WSM_FLOAT4 * 16);   // [warps][32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+
+    // B[k = co][n = ci] = W2[co][ci][tap]; thread (g,t) of n-tile j reads co = 4t..4t+3 for ci = 8j + g
+    for (int idx = tid; idx < WSM_FLOAT4; idx += MMA_THREADS) {
+        const int tap = idx >> 7, q = (idx >> 5) & 3, ln = idx & 31;
+        const int gg = ln >> 2, tt = ln & 3, j = q >> 1, lo_part = q & 1;
+        const int ci = 8 * j + gg;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float wv = __ldg(w + ((int64_t)(4 * tt + e) * C + ci) * NTAPS + tap);
+            const float hi = __uint_as_float(to_tf32(wv));
+            v[e] = lo_part ? __uint_as_float(to_tf32(wv - hi)) : hi;
+        }
+        wsm[idx] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    // BN1 constants of the thread's 4 output channels c = 8j + 2t + e
+    float k_mean[2][2], k_istd[2][2], k_a[2][2], k_b[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = 8 * j + 2 * t + e;
+            k_mean[j][e] = stat1[c]; k_istd[j][e] = stat1[C + c]; k_a[j][e] = stat1[2 * C + c]; k_b[j][e] = stat1[3 * C + c];
+        }
+    __syncthreads();
+
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int b = item / items_per_sample;
+        int r = item - b * items_per_sample;
+        DgradClass cl = dgrad_class(0, G1);
+        for (int cls = 0; cls < 8; ++cls) {                       // block-uniform
+            cl = dgrad_class(cls, G1);
+            if (r < cl.chunks) break;
+            r -= cl.chunks;
+        }
+        const int row0 = r * ROWS_PER_ITEM + warp * ROWS_PER_WARP;
+        // per row: dy2 offset of the (di,dj,dl) = (0,0,0) source voxel, output voxel index, validity bits
+        int src[MT][2], dst[MT][2];
+        uint32_t okb[MT][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int v = row0 + m * 16 + g + 8 * h;
+                const bool in = v < cl.nvox;
+                const int vv = in ? v : 0;
+                const int zi = vv % cl.nz, q = vv / cl.nz, yi = q % cl.ny, xi = q / cl.ny;
+                src[m][h] = ((xi * G2 + yi) * G2 + zi) * C;
+                dst[m][h] = in ? ((2 * xi + cl.cx) * G1 + (2 * yi + cl.cy)) * G1 + (2 * zi + cl.cz) : -1;
+                // bit 2a: source index (coordinate - 0) < G2;  bit 2a+1: (coordinate - 1) >= 0
+                uint32_t bits = 0;
+                if (in) {
+                    bits = (xi < G2 ? 1u : 0u) | (xi >= 1 ? 2u : 0u) | (yi < G2 ? 4u : 0u) | (yi >= 1 ? 8u : 0u) |
+                           (zi < G2 ? 16u : 0u) | (zi >= 1 ? 32u : 0u);
+                }
+                okb[m][h] = bits;
+            }
+        float acc[MT][2][4];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
+        const float* dy_b = dy2cl + (int64_t)b * P2 * C + 4 * t;
+
+        // taps of the class: per axis, parity 0 -> kernel offsets {0, 2} (source shift 0, 1); parity 1 -> {1} (shift 0)
+        const int nix = cl.cx ? 1 : 2, niy = cl.cy ? 1 : 2, niz = cl.cz ? 1 : 2;
+        for (int ax = 0; ax < nix; ++ax)
+            for (int ay = 0; ay < niy; ++ay)
+                for (int az = 0; az < niz; ++az) {
+                    const int i = cl.cx ? 1 : 2 * ax, jy = cl.cy ? 1 : 2 * ay, l = cl.cz ? 1 : 2 * az;
+                    const int tap = (i * 3 + jy) * 3 + l;
+                    const int delta = ((ax * G2 + ay) * G2 + az) * C;           // source shift (i>>1, j>>1, l>>1) = (ax, ay, az)
+                    const uint32_t need = (1u << ax) | (4u << ay) | (16u << az);
+                    const float4* wt = wsm + tap * 128 + lane;
+                    const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];
+                    const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
+                                               {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
+                    const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
+                                               {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
+                    float4 raw[MT][2];
+#pragma unroll
+                    for (int m = 0; m < MT; ++m)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            raw[m][h] = (okb[m][h] & need) == need
+                                            ? __ldg(reinterpret_cast<const float4*>(dy_b + src[m][h] - delta))
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const Split4 r0 = split4(raw[m][0]), r1 = split4(raw[m][1]);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const int e0 = 2 * ks, e1 = 2 * ks + 1;
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
+                                mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
+                                mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
+                            }
+                        }
+                    }
+                }
+
+        // ---- epilogue: ReLU mask from bn1(y1), store g1 (channels-last), BN1-backward partial sums
+        float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (dst[m][h] < 0) continue;
+                const int64_t base = ((int64_t)b * P1 + dst[m][h]) * C;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float2 yv = __ldg(reinterpret_cast<const float2*>(y1 + base + 8 * j + 2 * t));
+                    const float y2v[2] = {yv.x, yv.y};
+                    float o[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const float pre = fmaf(k_a[j][e], y2v[e], k_b[j][e]);
+                        const float gv = pre > 0.f ? acc[m][j][2 * h + e] : 0.f;
+                        o[e] = gv;
+                        s1[j][e] += gv;
+                        s2[j][e] = fmaf(gv, (y2v[e] - k_mean[j][e]) * k_istd[j][e], s2[j][e]);
+                    }
+                    *reinterpret_cast<float2*>(g1 + base + 8 * j + 2 * t) = make_float2(o[0], o[1]);
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float a = s1[j][e], q = s2[j][e];
+                a += __shfl_xor_sync(0xffffffffu, a, 4); a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+                q += __shfl_xor_sync(0xffffffffu, q, 4); q += __shfl_xor_sync(0xffffffffu, q, 8); q += __shfl_xor_sync(0xffffffffu, q, 16);
+                if (g == 0) { red[warp * 2 * C + 8 * j + 2 * t + e] = a; red[warp * 2 * C + C + 8 * j + 2 * t + e] = q; }
+            }
+        __syncthreads();
+        if (tid < 2 * C) {
+            float tot = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < MMA_WARPS; ++wv) tot += red[wv * 2 * C + tid];
+            bpart[(int64_t)item * 2 * C + tid] = tot;
+        }
+        __syncthreads();                                          // red[] is reused by the next item
+    }
+}
+
+}  // namespace
+
+int conv2_mma_chunks(int G2) { return (int)ceil_div((int64_t)G2 * G2 * G2, ROWS_PER_ITEM); }
+int conv2_mma_items(int B, int G2) { return B * conv2_mma_chunks(G2); }
+
+int launch_conv2_fwd_mma(const float* y1, const float* stat1, const float* w, const float* bias, float* y2, float* part,
+                         int B, int G1, int G2, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        attr_set = true;
+    }
+    const int chunks = conv2_mma_chunks(G2), items = B * chunks;
+    int sms = 148;
+    const int grid = std::min(items, sms * 3);
+    conv2_fwd_mma_kernel<<<grid, MMA_THREADS, MMA_SMEM, stream>>>(y1, stat1, w, bias, y2, part, G1, G2, chunks, items);
+    GNBV_LAUNCH_CHECK("conv2_fwd_mma_kernel");
+    return GNBV_OK;
+}
+
+int conv2_dgrad_mma_items_per_sample(int G1) {
+    int n = 0;
+    for (int cls = 0; cls < 8; ++cls) n += dgrad_class(cls, G1).chunks;
+    return n;
+}
+
+int launch_conv2_dgrad_mma(const float* dy2cl, const float* w, const float* y1, const float* stat1, float* g1, float* bpart,
+                           int B, int G1, int G2, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_dgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+        attr_set = true;
+    }
+    const int ips = conv2_dgrad_mma_items_per_sample(G1), items = B * ips;
+    conv2_dgrad_mma_kernel<<<std::min(items, 148 * 3), MMA_THREADS, MMA_SMEM, stream>>>(dy2cl, w, y1, stat1, g1, bpart, G1, G2, ips, items);
+    GNBV_LAUNCH_CHECK("conv2_dgrad_mma_kernel");
+    return GNBV_OK;
+}
+
+}  // namespace gnbv

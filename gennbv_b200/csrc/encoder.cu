@@ -15,6 +15,7 @@
 //     bf16 / tf32 operands, see gemm.cuh).
 #include "gemm.cuh"
 #include "conv2_tc.cuh"
+#include "conv2_mma.cuh"
 
 #include <stdlib.h>
 
@@ -30,6 +31,13 @@ constexpr int CONV2_ZT = 4;       // output voxels (along z) per thread
 
 
 constexpr int PART_STRIDE = 2 * C1 + 4;      // per block: mean[16], M2[16], count, pad
+
+// GNBV_CONV2_TC: 0 = CUDA-core conv2 kernels; 1 = tcgen05 forward (conv2_tc.cu); bit 2 = mma.sync forward, bit 4 = mma.sync
+// data gradient (conv2_mma.cu).  Read once per process.
+static int conv2_tc_mode() {
+    static const int mode = []() { const char* e = getenv("GNBV_CONV2_TC"); return e ? atoi(e) : 0; }();
+    return mode;
+}
 
 // Block-level (count, mean, M2) of `nv` values per thread and channel (acc[k][c], k < nv valid ones), written to
 // part[PART_STRIDE].  Two-pass inside each warp (mean first, then centred squares) and Chan's merge across warps:
@@ -1121,7 +1129,7 @@ EncDims make_dims(int B, int G, int state_dim) {
     d.items2 = d.G2 * d.G2 * (int)ceil_div(d.G2, CONV2_ZT);
     d.nblk2 = (int)ceil_div(d.items2, CONV2_THREADS);
     d.flat2 = (int64_t)C1 * d.P2;
-    d.nrec2 = std::max(d.nblk2, conv2_tc_supported(d.G1, d.G2) ? conv2_tc_tiles(1, d.G2) : 0);
+    d.nrec2 = std::max(std::max(d.nblk2, conv2_mma_chunks(d.G2)), conv2_tc_supported(d.G1, d.G2) ? conv2_tc_tiles(1, d.G2) : 0);
     return d;
 }
 
@@ -1130,7 +1138,7 @@ struct EncWs {
     size_t pe, h1, cat, y1, part1, stat1, y2, part2, stat2, act2, gemm, total;
     // backward-only
     size_t dz, dcat, dh1, dact2, dy2cl, g1, bn2part, coef2, bpart1, coef1, wg2part, wg1part;
-    int nblk_dg, nblk_wg2, nblk_wg1, wg2_pps, wg1_ips;
+    int nblk_dg, nrec_dg, nblk_wg2, nblk_wg1, wg2_pps, wg1_ips;
     int64_t wg1_items;
     size_t merge1, merge2, bmerge1;
 };
@@ -1160,6 +1168,7 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.bmerge1 = 0;
     w.dz = w.dcat = w.dh1 = w.dact2 = w.dy2cl = w.g1 = w.bn2part = w.coef2 = w.bpart1 = w.coef1 = w.wg2part = w.wg1part = 0;
     w.nblk_dg = (int)ceil_div((int64_t)d.G1 * d.G1 * 2 * ceil_div((d.G1 + 1) / 2, DG2_ZT), DG2_THREADS);
+    w.nrec_dg = std::max(w.nblk_dg, conv2_dgrad_mma_items_per_sample(d.G1));     // records per sample of either dgrad kernel
     w.wg2_pps = (int)std::max<int64_t>(1, ceil_div((int64_t)d.B * d.G2 * d.G2, (int64_t)WG2_MAX_BLOCKS));   // rows per block
     w.nblk_wg2 = (int)ceil_div((int64_t)d.B * d.G2 * d.G2, (int64_t)w.wg2_pps);
     w.wg1_items = (int64_t)d.B * d.G1 * d.G1 * ((d.G1 + 1) / 2);
@@ -1174,9 +1183,9 @@ EncWs make_ws(const EncDims& d, bool backward) {
         w.g1 = take(B * (size_t)d.P1 * C1);
         w.bn2part = take(B * C1 * 2);
         w.coef2 = take(2 * C1);
-        w.bpart1 = take(B * (size_t)w.nblk_dg * 2 * C1);
+        w.bpart1 = take(B * (size_t)w.nrec_dg * 2 * C1);
         w.coef1 = take(2 * C1);
-        w.bmerge1 = take((size_t)ceil_div(B * (size_t)w.nblk_dg, MERGE_FAN) * 2 * C1);
+        w.bmerge1 = take((size_t)ceil_div(B * (size_t)w.nrec_dg, MERGE_FAN) * 2 * C1);
         w.wg2part = take((size_t)w.nblk_wg2 * WG2_REC);
         w.wg1part = take((size_t)w.nblk_wg1 * WG1_REC);
         g = std::max(g, gemm_workspace_floats(d.B, 2 * d.HID, d.FEAT));
@@ -1269,9 +1278,16 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     // GNBV_CONV2_TC=1 routes conv2 through the tcgen05 tensor cores (3xTF32 implicit GEMM, conv2_tc.cu).  It is parity-green
     // but, with only N = 16 output channels per A element, its im2col + BN + split staging costs about as many
     // instructions as the CUDA-core kernel's FMAs (measured 1.43 ms vs 0.55 ms at B = 256), so it is opt-in this round.
-    static const bool use_tc = []() { const char* e = getenv("GNBV_CONV2_TC"); return e && e[0] == '1'; }();
+    // GNBV_CONV2_TC bit 2 (value 2) routes it through warp-level mma.sync with the same 3xTF32 split, operands taken from
+    // registers (conv2_mma.cu): no im2col staging at all.  Bit 4 does the same for the data gradient (value 6 = both).
+    const int tc_mode = conv2_tc_mode();
+    const bool use_tc = tc_mode == 1;
     int nrec2;
-    if (use_tc && conv2_tc_supported(d.G1, d.G2)) {
+    if (tc_mode & 2) {
+        rc = launch_conv2_fwd_mma(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2, part2, B, d.G1, d.G2, stream);
+        if (rc) return rc;
+        nrec2 = conv2_mma_items(B, d.G2);
+    } else if (use_tc && conv2_tc_supported(d.G1, d.G2)) {
         rc = launch_conv2_fwd_tc(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2, part2, nullptr, B, d.G1, d.G2, stream);
         if (rc) return rc;
         nrec2 = conv2_tc_tiles(B, d.G2);
@@ -1378,14 +1394,22 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);
     stage_mark(GNBV_ST_BWD_CONV2_DGRAD, stream);
-    conv2_dgrad_kernel<<<std::min(B * w.nblk_dg, 148 * 3), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1,
-                                                                                      ws + w.g1, ws + w.bpart1, d.G1, d.G2, w.nblk_dg,
-                                                                                      B * w.nblk_dg);
+    int nrec_dg;
+    if (conv2_tc_mode() & 4) {
+        rc = launch_conv2_dgrad_mma(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1, ws + w.bpart1, B, d.G1, d.G2, stream);
+        if (rc) return rc;
+        nrec_dg = B * conv2_dgrad_mma_items_per_sample(d.G1);
+    } else {
+        conv2_dgrad_kernel<<<std::min(B * w.nblk_dg, 148 * 3), DG2_THREADS, 0, stream>>>(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1,
+                                                                                          ws + w.g1, ws + w.bpart1, d.G1, d.G2, w.nblk_dg,
+                                                                                          B * w.nblk_dg);
+        nrec_dg = B * w.nblk_dg;
+    }
     GNBV_LAUNCH_CHECK("conv2_dgrad_kernel");
     stage_mark(GNBV_ST_BWD_BN1, stream);
     {
-        const int nm = (int)ceil_div((int64_t)B * w.nblk_dg, MERGE_FAN);
-        sum_merge_kernel<<<nm, 32 * C1, 0, stream>>>(ws + w.bpart1, B * w.nblk_dg, ws + w.bmerge1);
+        const int nm = (int)ceil_div((int64_t)nrec_dg, MERGE_FAN);
+        sum_merge_kernel<<<nm, 32 * C1, 0, stream>>>(ws + w.bpart1, nrec_dg, ws + w.bmerge1);
         bn_bwd_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.bmerge1, nm, 2 * C1, 1, (double)B * d.P1, gr->bn1_w, gr->bn1_b,
                                                           ws + w.coef1, training ? 0 : 1);
     }

@@ -47,6 +47,7 @@ GNBV_HD int nn_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi
 // meta from a bounding box (lo / hi per axis) and the requested resolution
 GNBV_HD void nn_make_meta(NNGridMeta& m, const float lo[3], const float hi[3], int n, int cells_per_axis) {
     float ext = 0.f;
+#pragma unroll
     for (int a = 0; a < 3; ++a) { m.lo[a] = lo[a]; ext = fmaxf(ext, hi[a] - lo[a]); }
     m.n = n;
     if (!(ext > 0.f) || n <= 0) {        // empty cloud, a single point or coincident points: one cell
@@ -55,11 +56,13 @@ GNBV_HD void nn_make_meta(NNGridMeta& m, const float lo[3], const float hi[3], i
     }
     m.h = ext / (float)cells_per_axis;
     m.inv_h = 1.f / m.h;
+#pragma unroll
     for (int a = 0; a < 3; ++a) m.dims[a] = nn_clampi((int)((hi[a] - lo[a]) * m.inv_h) + 1, 1, cells_per_axis);
 }
 
 GNBV_HD void nn_cell_of(const NNGridMeta& m, float x, float y, float z, int c[3]) {
     const float p[3] = {x, y, z};
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
         float t = floorf((p[a] - m.lo[a]) * m.inv_h);
         t = fminf(fmaxf(t, 0.f), (float)(m.dims[a] - 1));     // clamp in float first: far queries must not overflow int
@@ -89,6 +92,7 @@ GNBV_HD float nn_query(const NNGridMeta& m, const int* cell_end, const Float4* p
     int c[3];
     nn_cell_of(m, qx, qy, qz, c);
     int rmax = 0;
+#pragma unroll
     for (int a = 0; a < 3; ++a) {
         const int far = c[a] > m.dims[a] - 1 - c[a] ? c[a] : m.dims[a] - 1 - c[a];
         rmax = far > rmax ? far : rmax;

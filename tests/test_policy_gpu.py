@@ -223,14 +223,16 @@ def test_clip_and_adam_match_torch():
         assert float((p.cpu() - p_ref.detach()).abs().max()) <= 1e-6
 
 
-def test_tcgen05_conv2_path_is_parity_green():
-    """The opt-in tensor-core conv2 forward (GNBV_CONV2_TC=1, 3xTF32 implicit GEMM) reproduces the fp32 reference."""
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_tcgen05_conv2_path_is_parity_green(mode):
+    """The tensor-core conv2 forward paths (GNBV_CONV2_TC=1: tcgen05, =2: mma.sync; both 3xTF32 implicit GEMMs) reproduce
+    the fp32 reference in eval and in training mode (batch statistics come from the kernel's own records)."""
     import subprocess, sys, os
     code = (
         "import sys, os; sys.path[:0] = [%r, %r, %r]\n"
         "import torch, encoder_ref\n"
         "from test_policy_gpu import make_policy, rel_err\n"
-        "for G, B in ((64, 3), (20, 9)):\n"
+        "for G, B in ((64, 3), (20, 9), (20, 1)):\n"
         "    pol, ref, D = make_policy(G, 1)\n"
         "    g = torch.Generator().manual_seed(0)\n"
         "    obs = torch.zeros(B, D); obs[:, :600] = torch.randn(B, 600, generator=g)\n"
@@ -243,6 +245,20 @@ def test_tcgen05_conv2_path_is_parity_green():
         "print('tc-conv2 ok')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                                      os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
                                      os.path.dirname(os.path.abspath(__file__))))
-    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "GNBV_CONV2_TC": "1"}, capture_output=True, text=True,
+    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "GNBV_CONV2_TC": mode}, capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0 and "tc-conv2 ok" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("mode", ["2", "6"])
+def test_mma_conv2_kernels_pass_the_encoder_parity_tests(mode):
+    """GNBV_CONV2_TC=2 (mma.sync forward) / 6 (mma.sync forward + data gradient): the encoder forward/backward parity tests
+    against torch autograd (all grid sizes, eval and training BN) and the golden policy test are re-run in a subprocess
+    with the tensor-core kernels switched in."""
+    import subprocess, sys
+    here = os.path.abspath(__file__)
+    out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k",
+                          "encoder_forward_backward_vs_torch or policy_matches_reference_golden_g20"],
+                         env={**os.environ, "GNBV_CONV2_TC": mode}, capture_output=True, text=True, timeout=900,
+                         cwd=os.path.dirname(os.path.dirname(here)))
+    assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
