@@ -423,6 +423,101 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// conv2 weight gradient (same contract as conv2_wgrad_kernel in encoder.cu):
+//   dW2[co,ci,tap] = sum_{b,pos} dy2[b,pos,co] * relu(bn1(y1))[b, 2pos+tap, ci];   db2[co] = sum dy2[b,pos,co]
+// GEMM with M = 16 (co), N = 27 taps x 16 ci = 54 n-tiles of 8, K = output positions.  A block walks output z-rows
+// (b, x2, y2); a row's G2 positions are ceil(G2/8) k-steps (missing positions contribute zero A).  The four warps of a
+// block share the rows and split the taps (warp w owns taps w, w+4, ...: <= 7 taps x 2 ci-halves = 14 n-tiles = 56
+// accumulators), so every warp re-loads the small A fragment (dy2, 4 scalars per k-step) and its own B fragments
+// (activations: 2 scalars per n-tile and k-step, BN1 + ReLU + hi/lo split in registers).  Per block one record
+// part[blk][6912 + 16] in weight layout [co][ci][tap] followed by db2[16], reduced in fixed order by reduce_records_kernel.
+constexpr int WG_TAPS_PER_WARP = (NTAPS + MMA_WARPS - 1) / MMA_WARPS;       // 7
+constexpr int WG_REC = C * C * NTAPS + C;
+
+__device__ __forceinline__ void split1(float v, uint32_t& hi, uint32_t& lo) {
+    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+__global__ void __launch_bounds__(MMA_THREADS, 4)
+conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
+                       float* __restrict__ part, int G1, int G2, int total_rows, int rows_per_block) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    // BN1 scale / shift of the two input channels this lane supplies as B columns: ci = 8*hf + g
+    const float sc0 = stat1[2 * C + g], sh0 = stat1[3 * C + g], sc1 = stat1[2 * C + 8 + g], sh1 = stat1[3 * C + 8 + g];
+    float acc[WG_TAPS_PER_WARP][2][4];
+#pragma unroll
+    for (int k = 0; k < WG_TAPS_PER_WARP; ++k)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[k][hf][e] = 0.f;
+    float db_lo = 0.f, db_hi = 0.f;                          // sum of dy2 over positions for co = g and co = g + 8
+    const int ksteps = (G2 + 7) / 8;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(total_rows, r0 + rows_per_block);
+    for (int row = r0; row < r1; ++row) {
+        const int b = row / (G2 * G2), rem = row - b * G2 * G2, x2 = rem / G2, yy2 = rem - x2 * G2;
+        const float* dyrow = dy2cl + ((int64_t)b * P2 + (int64_t)(x2 * G2 + yy2) * G2) * C;
+        const float* xin = y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2) * G1 + 2 * yy2) * G1) * C;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int za = 8 * ks + t, zb = za + 4;             // positions of the fragment's k slots t and t + 4
+            const bool va = za < G2, vb = zb < G2;
+            const int zac = min(za, G2 - 1), zbc = min(zb, G2 - 1);
+            // A = dy2^T: a0 (co g, pos za), a1 (co g+8, pos za), a2 (co g, pos zb), a3 (co g+8, pos zb)
+            const float a0 = va ? __ldg(dyrow + zac * C + g) : 0.f, a1 = va ? __ldg(dyrow + zac * C + 8 + g) : 0.f;
+            const float a2 = vb ? __ldg(dyrow + zbc * C + g) : 0.f, a3 = vb ? __ldg(dyrow + zbc * C + 8 + g) : 0.f;
+            db_lo += a0 + a2; db_hi += a1 + a3;
+            uint32_t ah[4], al[4];
+            split1(a0, ah[0], al[0]); split1(a1, ah[1], al[1]); split1(a2, ah[2], al[2]); split1(a3, ah[3], al[3]);
+#pragma unroll
+            for (int k = 0; k < WG_TAPS_PER_WARP; ++k) {
+                const int tap = warp + MMA_WARPS * k;
+                if (tap < NTAPS) {                              // warp-uniform
+                    const int i = tap / 9, jy = (tap / 3) % 3, l = tap % 3;
+                    const float* line = xin + ((int64_t)(i * G1 + jy) * G1 + l) * C;
+                    // B (k = position, n = ci): b0 = x[2*za + l][ci], b1 = x[2*zb + l][ci]; clamped positions carry A = 0
+                    const float* pa = line + 2 * zac * C + g;
+                    const float* pb = line + 2 * zbc * C + g;
+                    const float x00 = fmaxf(fmaf(sc0, __ldg(pa), sh0), 0.f), x01 = fmaxf(fmaf(sc0, __ldg(pb), sh0), 0.f);
+                    const float x10 = fmaxf(fmaf(sc1, __ldg(pa + 8), sh1), 0.f), x11 = fmaxf(fmaf(sc1, __ldg(pb + 8), sh1), 0.f);
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split1(x00, bh0, bl0); split1(x01, bh1, bl1);
+                    mma_tf32(acc[k][0], al[0], al[1], al[2], al[3], bh0, bh1);
+                    mma_tf32(acc[k][0], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                    mma_tf32(acc[k][0], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                    split1(x10, bh0, bl0); split1(x11, bh1, bl1);
+                    mma_tf32(acc[k][1], al[0], al[1], al[2], al[3], bh0, bh1);
+                    mma_tf32(acc[k][1], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                    mma_tf32(acc[k][1], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                }
+            }
+        }
+    }
+    // ---- the block's record: acc (m = co, n = ci) -> [co][ci][tap]; db2 from warp 0
+    float* out = part + (int64_t)blockIdx.x * WG_REC;
+#pragma unroll
+    for (int k = 0; k < WG_TAPS_PER_WARP; ++k) {
+        const int tap = warp + MMA_WARPS * k;
+        if (tap < NTAPS) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int co = g + 8 * (e >> 1), ci = 8 * hf + 2 * t + (e & 1);
+                    out[(co * C + ci) * NTAPS + tap] = acc[k][hf][e];
+                }
+        }
+    }
+    if (warp == 0) {
+        db_lo += __shfl_xor_sync(0xffffffffu, db_lo, 1); db_lo += __shfl_xor_sync(0xffffffffu, db_lo, 2);
+        db_hi += __shfl_xor_sync(0xffffffffu, db_hi, 1); db_hi += __shfl_xor_sync(0xffffffffu, db_hi, 2);
+        if (t == 0) { out[C * C * NTAPS + g] = db_lo; out[C * C * NTAPS + 8 + g] = db_hi; }
+    }
+}
+
 }  // namespace
 
 int conv2_mma_chunks(int G2) { return (int)ceil_div((int64_t)G2 * G2 * G2, ROWS_PER_ITEM); }
@@ -459,6 +554,13 @@ int launch_conv2_dgrad_mma(const float* dy2cl, const float* w, const float* y1, 
     const int ips = conv2_dgrad_mma_items_per_sample(G1), items = B * ips;
     conv2_dgrad_mma_kernel<<<std::min(items, 148 * 3), MMA_THREADS, MMA_SMEM, stream>>>(dy2cl, w, y1, stat1, g1, bpart, G1, G2, ips, items);
     GNBV_LAUNCH_CHECK("conv2_dgrad_mma_kernel");
+    return GNBV_OK;
+}
+
+int launch_conv2_wgrad_mma(const float* y1, const float* stat1, const float* dy2cl, float* part, int B, int G1, int G2,
+                           int nblocks, int rows_per_block, cudaStream_t stream) {
+    conv2_wgrad_mma_kernel<<<nblocks, MMA_THREADS, 0, stream>>>(y1, stat1, dy2cl, part, G1, G2, B * G2 * G2, rows_per_block);
+    GNBV_LAUNCH_CHECK("conv2_wgrad_mma_kernel");
     return GNBV_OK;
 }
 

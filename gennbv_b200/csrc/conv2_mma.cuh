@@ -19,4 +19,9 @@ int conv2_dgrad_mma_items_per_sample(int G1);
 int launch_conv2_dgrad_mma(const float* dy2cl, const float* w, const float* y1, const float* stat1, float* g1, float* bpart,
                            int B, int G1, int G2, cudaStream_t stream);
 
+// conv2 weight gradient (contract of conv2_wgrad_kernel): block blk reduces output z-rows [blk*rows_per_block, ...) and
+// writes part[blk][16*16*27 + 16] ([co][ci][tap] followed by db2[16]).
+int launch_conv2_wgrad_mma(const float* y1, const float* stat1, const float* dy2cl, float* part, int B, int G1, int G2,
+                           int nblocks, int rows_per_block, cudaStream_t stream);
+
 }  // namespace gnbv

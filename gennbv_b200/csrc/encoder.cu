@@ -33,7 +33,7 @@ constexpr int CONV2_ZT = 4;       // output voxels (along z) per thread
 constexpr int PART_STRIDE = 2 * C1 + 4;      // per block: mean[16], M2[16], count, pad
 
 // GNBV_CONV2_TC: 0 = CUDA-core conv2 kernels; 1 = tcgen05 forward (conv2_tc.cu); bit 2 = mma.sync forward, bit 4 = mma.sync
-// data gradient (conv2_mma.cu).  Read once per process.
+// data gradient, bit 8 = mma.sync weight gradient (conv2_mma.cu); 14 = all three.  Read once per process.
 static int conv2_tc_mode() {
     static const int mode = []() { const char* e = getenv("GNBV_CONV2_TC"); return e ? atoi(e) : 0; }();
     return mode;
@@ -1388,8 +1388,13 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     const size_t smem_wg2 = std::max(3 * (size_t)WG2_REC, 2 * (9 * line_f + dyl_f)) * 4;
     GNBV_REQUIRE(smem_wg2 <= 200 * 1024, "gnbv_encoder_backward: grid too large for the conv2 wgrad staging buffers");
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
-    conv2_wgrad_kernel<<<w.nblk_wg2, WG2_THREADS, smem_wg2, stream>>>(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, d.G1,
-                                                                       d.G2, B * d.G2 * d.G2, w.wg2_pps);
+    if (conv2_tc_mode() & 8) {
+        rc = launch_conv2_wgrad_mma(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, w.wg2_pps, stream);
+        if (rc) return rc;
+    } else {
+        conv2_wgrad_kernel<<<w.nblk_wg2, WG2_THREADS, smem_wg2, stream>>>(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, d.G1,
+                                                                           d.G2, B * d.G2 * d.G2, w.wg2_pps);
+    }
     GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
     reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);

@@ -250,9 +250,9 @@ def test_tcgen05_conv2_path_is_parity_green(mode):
     assert out.returncode == 0 and "tc-conv2 ok" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("mode", ["2", "6"])
+@pytest.mark.parametrize("mode", ["2", "6", "14"])
 def test_mma_conv2_kernels_pass_the_encoder_parity_tests(mode):
-    """GNBV_CONV2_TC=2 (mma.sync forward) / 6 (mma.sync forward + data gradient): the encoder forward/backward parity tests
+    """GNBV_CONV2_TC=2 (mma.sync forward) / 6 (+ data gradient) / 14 (+ weight gradient): the encoder forward/backward parity tests
     against torch autograd (all grid sizes, eval and training BN) and the golden policy test are re-run in a subprocess
     with the tensor-core kernels switched in."""
     import subprocess, sys
