@@ -352,8 +352,12 @@ def run_native(args, rank, world):
                      "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_grid,
                      "voxelize_algorithmic_bytes_per_step": N * (b_vox + b_cov)},
-        "compute_kernels": {"note": "fp32 CUDA-core contractions (1e-4 parity budget rules out bf16/tf32 operands); nominal "
-                                    "fp32 peak %.1f TFLOP/s; tensor-pipe utilisation is 0 by design this round" % fp32_peak,
+        "compute_kernels": {"note": "conv2 forward / dgrad / wgrad run on the tensor cores as mma.sync 3xTF32 implicit GEMMs "
+                                    "(GNBV_CONV2_TC=%s; plain tf32/bf16 operands would break the 1e-4 parity budget, the "
+                                    "hi/lo split keeps fp32-level error at 3 MMAs per product); conv1 and the Linear layers "
+                                    "are fp32 CUDA-core kernels.  tflops = ALGORITHMIC fp32 flops / time, against the nominal "
+                                    "fp32 FMA peak %.1f TFLOP/s (no measured denominator exists for it)"
+                                    % (os.environ.get("GNBV_CONV2_TC", "14 (default)"), fp32_peak),
                             "kernels": compute},
         "e2e": {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},

@@ -7,6 +7,8 @@ Same interface: `reset()`, `add(obs, action, reward, episode_start, value, log_p
 B200-first differences:
   * storage is allocated once ([T,N,D] fp32 = 35.5 GB at 64^3 fits the 180 GB HBM3e) instead of being re-created by
     every reset() (buffers.py:659-673);
+  * `add()` skips the observation copy when the env already wrote the observation into this slot
+    (`Env_Train_GenNBV.bind_next_observation`, used by `PPO_Grid_Obs.collect_rollouts`);
   * GAE is one kernel launch (gnbv_gae) instead of a Python loop of T x 8 launches (:706-724);
   * `get()` does not materialise swap_and_flatten's transposed copy of the observations (:56-69,736-746): the
     reference's env-major flat index i = n*T + t is mapped to the storage row t*N + n, and `minibatch_rows()` hands
@@ -65,7 +67,8 @@ class TensorRolloutBuffer_Grid_Obs:
         if self.step >= self.buffer_size:
             raise AssertionError("Rollout buffer overflow")
         t = self.step
-        self.observations[t].copy_(obs)
+        if obs.data_ptr() != self.observations[t].data_ptr():      # already in place when the env wrote it there (8f-2)
+            self.observations[t].copy_(obs)
         self.actions[t].copy_(action)
         self.rewards[t].copy_(reward.view(-1, 1))
         self.episode_starts[t].copy_(episode_start.view(-1, 1))

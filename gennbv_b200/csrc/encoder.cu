@@ -32,10 +32,12 @@ constexpr int CONV2_ZT = 4;       // output voxels (along z) per thread
 
 constexpr int PART_STRIDE = 2 * C1 + 4;      // per block: mean[16], M2[16], count, pad
 
-// GNBV_CONV2_TC: 0 = CUDA-core conv2 kernels; 1 = tcgen05 forward (conv2_tc.cu); bit 2 = mma.sync forward, bit 4 = mma.sync
-// data gradient, bit 8 = mma.sync weight gradient (conv2_mma.cu); 14 = all three.  Read once per process.
+// GNBV_CONV2_TC selects the conv2 kernels (bit mask, read once per process).  Default 14 = the three mma.sync 3xTF32
+// kernels of conv2_mma.cu (bit 2 forward, bit 4 data gradient, bit 8 weight gradient): measured on B200 at B = 256, 64^3:
+// forward 0.557 -> 0.283 ms, dgrad 0.838 -> 0.602 ms, wgrad 0.699 -> 0.581 ms against the CUDA-core kernels (profiles/r01p).
+// 0 = CUDA-core kernels; 1 = tcgen05 forward (conv2_tc.cu, slower: staging-bound).  All variants are parity-green.
 static int conv2_tc_mode() {
-    static const int mode = []() { const char* e = getenv("GNBV_CONV2_TC"); return e ? atoi(e) : 0; }();
+    static const int mode = []() { const char* e = getenv("GNBV_CONV2_TC"); return e ? atoi(e) : 14; }();
     return mode;
 }
 

@@ -117,6 +117,7 @@ class Env_Train_GenNBV:
         self._obs_pp = [torch.zeros(N, self.obs_dim, device=dev) for _ in range(2)]
         self._dones_pp = [torch.zeros(N, dtype=torch.uint8, device=dev) for _ in range(2)]
         self._pp = 0
+        self._obs_target = None
         self.obs_flat = self._obs_pp[0]
         self._dones_u8 = self._dones_pp[0]
         self._cov_sum = torch.zeros(N, device=dev)
@@ -242,6 +243,15 @@ class Env_Train_GenNBV:
         c2w[:, :3, 3] -= self.env_origins
         return c2w.contiguous().to(self.device, non_blocking=True)
 
+    def bind_next_observation(self, target):
+        """The next step()/reset() writes its flattened observation [N, D] straight into `target` (e.g. the rollout
+        buffer's slot for the next transition) instead of the env's own ping-pong buffer; the returned
+        observation is then a view of `target`.  One-shot; every column of the row is rewritten by the step."""
+        if not (isinstance(target, torch.Tensor) and target.is_cuda and target.dtype == torch.float32 and target.is_contiguous()
+                and tuple(target.shape) == (self.num_envs, self.obs_dim)):
+            raise RuntimeError(f"bind_next_observation: expected a contiguous float32 CUDA tensor [{self.num_envs}, {self.obs_dim}]")
+        self._obs_target = target
+
     # hooks of the eval env (gennbv_b200/env_eval.py); no-ops here
     def _after_occ_grid_update(self, frame, c2w):
         pass
@@ -254,6 +264,8 @@ class Env_Train_GenNBV:
         L, s, N, G = _lib.lib(), ops._stream(), self.num_envs, self.grid_size
         self._pp ^= 1
         self.obs_flat, self._dones_u8 = self._obs_pp[self._pp], self._dones_pp[self._pp]
+        if self._obs_target is not None:                 # one-shot: this step's observation is born in the caller's storage
+            self.obs_flat, self._obs_target = self._obs_target, None
         frame = self.sensor.render(self.poses)
         self._frame = frame
         c2w = self._c2w(frame)

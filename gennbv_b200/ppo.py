@@ -51,6 +51,7 @@ class PPO_Grid_Obs:
         self.max_grad_norm, self.target_kl = max_grad_norm, target_kl
         self.policy_class, self.policy_kwargs = policy, dict(policy_kwargs or {})
         self.seed, self.verbose = seed, verbose
+        self.bind_rollout_slots = True                       # observations are written straight into the buffer
         self.pg_coef = 10.0                                  # ppo_grid_obs.py:253 (`policy_loss * 10`)
         self.num_timesteps = self._n_updates = 0
         self._current_progress_remaining = 1.0
@@ -108,8 +109,11 @@ class PPO_Grid_Obs:
         # so the features extracted for the bootstrap are reused for the next action.  Results are identical.
         with torch.no_grad():
             feats = self.policy.extract_features(self._last_obs)
+        bind = getattr(env, "bind_next_observation", None) if self.bind_rollout_slots else None
         while n_steps < n_rollout_steps:
             actions, values, log_probs = self.policy.act_from_features(feats)
+            if bind is not None and n_steps + 1 < min(n_rollout_steps, buf.buffer_size):
+                bind(buf.observations[n_steps + 1])          # new_obs is born in the slot the next add() would copy it to
             new_obs, rewards, dones, infos = env.step(actions)
             self.num_timesteps += env.num_envs
             if callback is not None and callback(locals()) is False:

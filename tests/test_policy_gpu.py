@@ -250,11 +250,12 @@ def test_tcgen05_conv2_path_is_parity_green(mode):
     assert out.returncode == 0 and "tc-conv2 ok" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("mode", ["2", "6", "14"])
-def test_mma_conv2_kernels_pass_the_encoder_parity_tests(mode):
-    """GNBV_CONV2_TC=2 (mma.sync forward) / 6 (+ data gradient) / 14 (+ weight gradient): the encoder forward/backward parity tests
-    against torch autograd (all grid sizes, eval and training BN) and the golden policy test are re-run in a subprocess
-    with the tensor-core kernels switched in."""
+@pytest.mark.parametrize("mode", ["0", "2", "6"])
+def test_every_conv2_kernel_variant_passes_the_encoder_parity_tests(mode):
+    """The default is GNBV_CONV2_TC=14 (mma.sync forward + data gradient + weight gradient, exercised by every other test in
+    this file).  Here the encoder forward/backward parity tests against torch autograd (all grid sizes, eval and training
+    BN) and the golden policy test are re-run in a subprocess with 0 (the CUDA-core kernels), 2 (mma.sync forward only)
+    and 6 (forward + data gradient), so that every kernel variant and every mix stays parity-green."""
     import subprocess, sys
     here = os.path.abspath(__file__)
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k",

@@ -77,6 +77,32 @@ def test_collect_rollouts_fills_buffer_like_the_reference_loop():
     np.testing.assert_array_equal(batch.advantages.cpu().numpy(), buf.advantages[t, n, 0].cpu().numpy())
 
 
+def test_rollout_observations_are_born_in_the_buffer_slots():
+    """with `bind_rollout_slots` the env writes step t's observation straight into buffer slot t+1 (add() then
+    skips its copy); the buffer content is identical to the copying path."""
+    g = EnvGolden("env_g20_long")
+    T = 10
+    bufs = []
+    for bind in (True, False):
+        env = EnvWrapperGenNBVTrain(make_env(g))
+        algo, _ = make_algo(env, n_steps=T, batch_size=9, n_epochs=1)
+        algo.bind_rollout_slots = bind
+        algo._setup_learn()
+        ptrs = []
+        assert algo.collect_rollouts(callback=lambda loc: ptrs.append(loc["new_obs"].data_ptr()))
+        buf = algo.rollout_buffer
+        slots = [buf.observations[t].data_ptr() for t in range(T)]
+        if bind:
+            assert ptrs[:T - 1] == slots[1:], "observations of steps 0..T-2 must live in slots 1..T-1"
+            assert ptrs[T - 1] not in slots               # the last one stays in the env's own buffer for the next rollout
+        else:
+            assert not set(ptrs) & set(slots)
+        bufs.append({k: getattr(buf, k).clone() for k in ("observations", "actions", "rewards", "episode_starts", "values",
+                                                          "log_probs", "advantages", "returns")})
+    for k in bufs[0]:
+        assert torch.equal(bufs[0][k], bufs[1][k]), k
+
+
 @pytest.mark.parametrize("target_kl", [None, 1e-7])
 def test_fused_train_matches_torch_rerun(target_kl):
     g = EnvGolden("env_g20_long")
