@@ -38,19 +38,33 @@ def default_cells_per_axis(n_ref):
 
 
 def chamfer_terms(xs, ys, method="auto", cells_per_axis=None, return_min=False):
-    """Per-cloud one-directional terms (mean_i min_j d^2, mean_j min_i d^2) as two [E] tensors.
+    """Per-cloud one-directional terms (mean_i min_j d^2, mean_j min_i d^2) as two [E] tensors, for lists of clouds.
 
     method: "brute" (P1*P2 scan, gnbv_chamfer), "grid" (exact uniform-grid search, gnbv_chamfer_grid) or "auto"
     (grid once a cloud pair has >= GRID_MIN_PAIRS pairs).  With return_min=True the per-point minima (two packed
     [sum P] tensors) are returned as well."""
-    E, dev = len(xs), xs[0].device
+    dev = xs[0].device
     if dev.type != "cuda":
         raise RuntimeError("chamfer_distance: expected CUDA tensors (no CPU path)")
+    xp, _, nx = _pack(xs, dev)
+    yp, _, ny = _pack(ys, dev)
+    return chamfer_terms_packed(xp, nx, yp, ny, method=method, cells_per_axis=cells_per_axis, return_min=return_min)
+
+
+def chamfer_terms_packed(xp, nx, yp, ny, method="auto", cells_per_axis=None, return_min=False):
+    """Same for clouds that are already packed: xp [sum nx, 3] / yp [sum ny, 3] float32 CUDA tensors, nx / ny the per-cloud
+    point counts (host lists)."""
+    E, dev = len(nx), xp.device
+    if dev.type != "cuda":
+        raise RuntimeError("chamfer_distance: expected CUDA tensors (no CPU path)")
+    if len(ny) != E or xp.shape[0] != sum(nx) or yp.shape[0] != sum(ny):
+        raise ValueError("packed clouds and their sizes do not match")
     if method not in ("auto", "brute", "grid"):
         raise ValueError(f"unknown method {method!r}")
     L, s = _lib.lib(), ops._stream()
-    xp, xo, nx = _pack(xs, dev)
-    yp, yo, ny = _pack(ys, dev)
+    xp, yp = xp.float().contiguous(), yp.float().contiguous()
+    offs = lambda n: torch.tensor([0] + list(torch.tensor(n, dtype=torch.int64).cumsum(0)), dtype=torch.int64, device=dev)
+    xo, yo = offs(nx), offs(ny)
     if method == "auto":
         method = "grid" if max(a * b for a, b in zip(nx, ny)) >= GRID_MIN_PAIRS else "brute"
     cx, cy = torch.empty(E, device=dev), torch.empty(E, device=dev)

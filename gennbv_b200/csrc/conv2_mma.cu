@@ -17,6 +17,7 @@
 // exactly the order the threads read them: [tap][ntile*2 + part][lane] as float4 -> conflict-free LDS.128.
 #include "common.cuh"
 #include "conv2_mma.cuh"
+#include "mma.cuh"
 
 #include <algorithm>
 
@@ -34,18 +35,6 @@ constexpr int ROWS_PER_ITEM = ROWS_PER_WARP * MMA_WARPS;   // 256 output voxels 
 constexpr int WSM_FLOAT4 = NTAPS * 4 * 32;          // 3456 float4 = 55,296 B
 constexpr int MMA_PART_STRIDE = 2 * C + 4;          // == PART_STRIDE of encoder.cu: mean[16], M2[16], count, pad
 constexpr size_t MMA_SMEM = (size_t)WSM_FLOAT4 * 16 + (size_t)(2 * MMA_WARPS * C + C) * 4;
-
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
 
 struct Split4 { uint32_t hi[4], lo[4]; };
 
@@ -436,11 +425,6 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
 constexpr int WG_TAPS_PER_WARP = (NTAPS + MMA_WARPS - 1) / MMA_WARPS;       // 7
 constexpr int WG_REC = C * C * NTAPS + C;
 
-__device__ __forceinline__ void split1(float v, uint32_t& hi, uint32_t& lo) {
-    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
-    lo = __float_as_uint(v - __uint_as_float(hi));
-}
-
 __global__ void __launch_bounds__(MMA_THREADS, 4)
 conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
                        float* __restrict__ part, int G1, int G2, int total_rows, int rows_per_block) {
@@ -471,7 +455,7 @@ conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ s
             const float a2 = vb ? __ldg(dyrow + zbc * C + g) : 0.f, a3 = vb ? __ldg(dyrow + zbc * C + 8 + g) : 0.f;
             db_lo += a0 + a2; db_hi += a1 + a3;
             uint32_t ah[4], al[4];
-            split1(a0, ah[0], al[0]); split1(a1, ah[1], al[1]); split1(a2, ah[2], al[2]); split1(a3, ah[3], al[3]);
+            split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]); split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
 #pragma unroll
             for (int k = 0; k < WG_TAPS_PER_WARP; ++k) {
                 const int tap = warp + MMA_WARPS * k;
@@ -484,11 +468,11 @@ conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ s
                     const float x00 = fmaxf(fmaf(sc0, __ldg(pa), sh0), 0.f), x01 = fmaxf(fmaf(sc0, __ldg(pb), sh0), 0.f);
                     const float x10 = fmaxf(fmaf(sc1, __ldg(pa + 8), sh1), 0.f), x11 = fmaxf(fmaf(sc1, __ldg(pb + 8), sh1), 0.f);
                     uint32_t bh0, bl0, bh1, bl1;
-                    split1(x00, bh0, bl0); split1(x01, bh1, bl1);
+                    split_tf32(x00, bh0, bl0); split_tf32(x01, bh1, bl1);
                     mma_tf32(acc[k][0], al[0], al[1], al[2], al[3], bh0, bh1);
                     mma_tf32(acc[k][0], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
                     mma_tf32(acc[k][0], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-                    split1(x10, bh0, bl0); split1(x11, bh1, bl1);
+                    split_tf32(x10, bh0, bl0); split_tf32(x11, bh1, bl1);
                     mma_tf32(acc[k][1], al[0], al[1], al[2], al[3], bh0, bh1);
                     mma_tf32(acc[k][1], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
                     mma_tf32(acc[k][1], ah[0], ah[1], ah[2], ah[3], bh0, bh1);

@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "conv2_tc.cuh"
 #include "conv2_mma.cuh"
+#include "mma.cuh"
 
 #include <stdlib.h>
 
@@ -38,6 +39,12 @@ constexpr int PART_STRIDE = 2 * C1 + 4;      // per block: mean[16], M2[16], cou
 // 0 = CUDA-core kernels; 1 = tcgen05 forward (conv2_tc.cu, slower: staging-bound).  All variants are parity-green.
 static int conv2_tc_mode() {
     static const int mode = []() { const char* e = getenv("GNBV_CONV2_TC"); return e ? atoi(e) : 14; }();
+    return mode;
+}
+
+// GNBV_CONV1_MMA: bit 1 = conv1 forward on the tensor cores (conv1_fwd_mma_kernel), bit 2 = conv1 weight gradient.
+static int conv1_mma_mode() {
+    static const int mode = []() { const char* e = getenv("GNBV_CONV1_MMA"); return e ? atoi(e) : 0; }();
     return mode;
 }
 
@@ -1062,6 +1069,372 @@ conv1_fwd_tma_kernel(const float* __restrict__ obs, int64_t obs_stride, const in
     if (!ok) { asm volatile("trap;"); }
 }
 
+// conv1 weight gradient on the tensor cores, same staging, contract and per-block record as conv1_wgrad_tma_kernel:
+//   dy1 = a1 * (g1 - S1/n - xhat1 * S2/n);  dW1[co,tap] = sum dy1[b,p,co] * tri[b, 2p+tap];  db1[co] = sum dy1
+// GEMM with M = 16 (co), N = 27 taps padded to 32 (4 n-tiles), K = output positions: a k-step is 8 consecutive z1 of one
+// staged y-row.  A = dy1^T is formed in registers from the staged g1 / y1 rows (BN1 backward on the fly) and split hi/lo;
+// B = the tri-class input, exact in TF32 (checked like the forward kernel: a row block whose inputs are not TF32 numbers is
+// redone with B split too).  The 8 warps of a block take different k-steps and their 16-register accumulators are
+// combined through shared memory at the end, exactly like the CUDA-core kernel's record.
+constexpr int C1M_THREADS = 256;
+constexpr int C1M_WARPS = C1M_THREADS / 32;
+
+template <bool SPLIT_B>
+__device__ __forceinline__ uint32_t conv1_wgrad_mma_rowblock(const float* __restrict__ ts, const float* __restrict__ gs,
+                                                              const float* __restrict__ ys, int G, int G1, int TL, int nr,
+                                                              const float (&kc)[2][5], const int (&boff)[4],
+                                                              float (&acc)[4][4], float (&dbs)[2]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int KS = (G1 + 7) / 8, nks = nr * KS;
+    uint32_t orbits = 0;
+    for (int ks = warp; ks < nks; ks += C1M_WARPS) {
+        const int r = ks / KS, z0 = 8 * (ks - r * KS);
+        const int za = z0 + t, zb = za + 4;
+        const bool va = za < G1, vb = zb < G1;
+        const int zac = min(za, G1 - 1), zbc = min(zb, G1 - 1);
+        // A = dy1^T: a0 (co g, pos za), a1 (co g+8, pos za), a2 (co g, pos zb), a3 (co g+8, pos zb)
+        float av[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int h = q & 1, zc = (q >> 1) ? zbc : zac;
+            const bool valid = (q >> 1) ? vb : va;
+            const int idx = (r * G1 + zc) * C1 + g + 8 * h;
+            const float dy = kc[h][2] * (gs[idx] - kc[h][3] - ((ys[idx] - kc[h][0]) * kc[h][1]) * kc[h][4]);
+            av[q] = valid ? dy : 0.f;
+        }
+        dbs[0] += av[0] + av[2];
+        dbs[1] += av[1] + av[3];
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) split_tf32(av[q], ah[q], al[q]);
+        // B (k = position, n = tap 8j + g): input voxel (2r + jj, 2z + l) of slab i
+        const float* pa = ts + (2 * r) * G + 2 * zac;
+        const float* pb = ts + (2 * r) * G + 2 * zbc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float x0 = pa[boff[j]], x1 = pb[boff[j]];
+            if (SPLIT_B) {
+                uint32_t h0, l0, h1, l1;
+                split_tf32(x0, h0, l0); split_tf32(x1, h1, l1);
+                mma_tf32(acc[j], al[0], al[1], al[2], al[3], h0, h1);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], l0, l1);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], h0, h1);
+            } else {
+                const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1);
+                orbits |= b0 | b1;
+                mma_tf32(acc[j], al[0], al[1], al[2], al[3], b0, b1);
+                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], b0, b1);
+            }
+        }
+    }
+    return orbits & 0x1fffu;
+}
+
+__global__ void __launch_bounds__(C1M_THREADS)
+conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
+                       const float* __restrict__ g1, const float* __restrict__ y1, const float* __restrict__ stat1,
+                       const float* __restrict__ coef, float* __restrict__ part, int G, int G1, int total_rb, int rb_per_block) {
+    extern __shared__ __align__(128) float dsm[];
+    __shared__ float red[C1M_WARPS][WG1_REC];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int P1 = G1 * G1 * G1, NYB = (G1 + WG1_RB - 1) / WG1_RB;
+    const int TL = (2 * WG1_RB + 1) * G;                    // floats per staged tri slab
+    const int GL = WG1_RB * G1 * C1;                        // floats per staged g1 / y1 slab
+    const int STAGE = 3 * TL + 2 * GL;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+    float dbs[2] = {0.f, 0.f};
+    float kc[2][5];                                         // channels g, g + 8: mean, invstd, a1, S1/n, S2/n
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int c = g + 8 * h;
+        kc[h][0] = stat1[c]; kc[h][1] = stat1[C1 + c]; kc[h][2] = stat1[2 * C1 + c]; kc[h][3] = coef[c]; kc[h][4] = coef[C1 + c];
+    }
+    int boff[4];                                            // slab offset of tap n = 8j + g (padding taps alias tap 26)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int tc = min(8 * j + g, TAPS - 1);
+        boff[j] = (tc / 9) * TL + ((tc / 3) % 3) * G + tc % 3;
+    }
+    const int rb0 = blockIdx.x * rb_per_block, rb1 = min(total_rb, rb0 + rb_per_block);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int rb, int& b, int& x1, int& y0, int& nr) {
+        b = rb / (G1 * NYB);
+        const int rem = rb - b * G1 * NYB;
+        x1 = rem / NYB;
+        y0 = (rem - x1 * NYB) * WG1_RB;
+        nr = min(WG1_RB, G1 - y0);
+    };
+    auto issue = [&](int rb, int stage) {                   // thread 0 only
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * STAGE);
+        const uint32_t tri_bytes = (uint32_t)(2 * nr + 1) * G * 4, g_bytes = (uint32_t)nr * G1 * C1 * 4;
+        mbar_expect_tx(bar, 3 * tri_bytes + 2 * g_bytes);
+        const float* orow = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            bulk_g2s(dst + (uint32_t)(i * TL * 4), orow + ((int64_t)(2 * x1 + i) * G + 2 * y0) * G, tri_bytes, bar);
+        const int64_t goff = ((int64_t)b * P1 + ((int64_t)x1 * G1 + y0) * G1) * C1;
+        bulk_g2s(dst + (uint32_t)(3 * TL * 4), g1 + goff, g_bytes, bar);
+        bulk_g2s(dst + (uint32_t)((3 * TL + GL) * 4), y1 + goff, g_bytes, bar);
+    };
+    if (tid == 0 && rb0 < rb1) issue(rb0, 0);
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    for (int rb = rb0; rb < rb1; ++rb) {
+        const int stage = (rb - rb0) & 1;
+        if (tid == 0 && rb + 1 < rb1) issue(rb + 1, stage ^ 1);
+        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
+        phase[stage] ^= 1;
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const float* ts = dsm + stage * STAGE;
+        const float* gs = ts + 3 * TL;
+        const float* ys = gs + GL;
+        float keep[4][4], keep_db[2] = {dbs[0], dbs[1]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) keep[j][e] = acc[j][e];
+        const uint32_t inexact = conv1_wgrad_mma_rowblock<false>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
+        if (__syncthreads_or((int)inexact)) {               // some input value is not a TF32 number: redo with B split
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[j][e] = keep[j][e];
+            dbs[0] = keep_db[0]; dbs[1] = keep_db[1];
+            conv1_wgrad_mma_rowblock<true>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
+        }
+        __syncthreads();
+    }
+    if (!ok) { asm volatile("trap;"); }
+    // accumulators: c0 (co g, tap 8j+2t), c1 (co g, tap 8j+2t+1), c2 (co g+8, tap 8j+2t), c3 (co g+8, tap 8j+2t+1)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int co = g + 8 * (e >> 1), tap = 8 * j + 2 * t + (e & 1);
+            if (tap < TAPS) red[wid][co * TAPS + tap] = acc[j][e];
+        }
+    {
+        float d0 = dbs[0], d1 = dbs[1];
+        d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+        if (t == 0) { red[wid][C1 * TAPS + g] = d0; red[wid][C1 * TAPS + 8 + g] = d1; }
+    }
+    __syncthreads();
+    for (int j = tid; j < WG1_REC; j += C1M_THREADS) {
+        float tsum = 0.f;
+#pragma unroll
+        for (int w = 0; w < C1M_WARPS; ++w) tsum += red[w][j];
+        part[(int64_t)blockIdx.x * WG1_REC + j] = tsum;
+    }
+}
+
+// conv1 forward on the tensor cores (mma.sync m16n8k8, TF32 operands, fp32 accumulation), same staging and contract as
+// conv1_fwd_tma_kernel.  GEMM rows = output voxels (16 consecutive z1 of one y-row per m-tile), K = 27 taps padded to 32
+// (4 k-steps), N = 16 channels.  The weights are split hi/lo once into REGISTER-resident B fragments (w = hi + lo, 2^-22
+// relative); the input is the tri-class grid, whose values {-1, 0, 1} are exact in TF32, so one A fragment (plain LDS.32
+// from the staged slabs, no conversion) feeds two MMAs per k-step and n-tile: 16 LDS + 16 HMMA per 16 voxels instead of
+// 432 FMA per voxel.  Exactness of A is CHECKED, not assumed: the low 13 mantissa bits of everything loaded are OR-ed
+// together, and a row block that held anything not representable in TF32 is recomputed with the A operand split as
+// well (3 MMAs, SPLIT_A = true) -- arbitrary float grids stay at fp32-level accuracy, ternary grids never take that path.
+// BN statistics: per-thread shifted sums (shift = bias, the value of every voxel whose neighbourhood is unknown space)
+// -> (n, mean, M2) -> Chan merges across lanes, warps and (bn_merge_kernel) blocks.
+__device__ __forceinline__ void chan_merge_f(float& n, float& mean, float& M2, float nb, float mb, float M2b) {
+    if (nb > 0.f) {
+        const float nt = n + nb, delta = mb - mean, f = nb / nt;
+        mean = fmaf(delta, f, mean);
+        M2 += M2b + delta * delta * n * f;
+        n = nt;
+    }
+}
+
+template <bool SPLIT_A>
+__device__ __forceinline__ uint32_t conv1_mma_rowblock(const float* __restrict__ ts, int G, int G1, int nr, int64_t out_base,
+                                                        float* __restrict__ y1, const uint32_t (&bh)[4][2][2],
+                                                        const uint32_t (&bl)[4][2][2], const int (&toff)[4][2],
+                                                        const float (&bias_r)[2][2], float (&S1)[2][2], float (&S2)[2][2],
+                                                        float& cnt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const int ZT = (G1 + 15) / 16, ntiles = nr * ZT;
+    uint32_t orbits = 0;
+    for (int tile = warp; tile < ntiles; tile += C1M_WARPS) {
+        const int r = tile / ZT, z0 = 16 * (tile - r * ZT);
+        // corner of the receptive field of rows g / g + 8 in slab i = 0 (rows past G1 alias the last voxel; never stored)
+        const float* pa = ts + (2 * r) * G + 2 * min(z0 + g, G1 - 1);
+        const float* pb = ts + (2 * r) * G + 2 * min(z0 + g + 8, G1 - 1);
+        float acc[2][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[j][0] = acc[j][2] = bias_r[j][0]; acc[j][1] = acc[j][3] = bias_r[j][1]; }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            const uint32_t a0 = __float_as_uint(pa[toff[s][0]]), a1 = __float_as_uint(pb[toff[s][0]]);
+            const uint32_t a2 = __float_as_uint(pa[toff[s][1]]), a3 = __float_as_uint(pb[toff[s][1]]);
+            if (SPLIT_A) {
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_tf32(__uint_as_float(a0), h0, l0); split_tf32(__uint_as_float(a1), h1, l1);
+                split_tf32(__uint_as_float(a2), h2, l2); split_tf32(__uint_as_float(a3), h3, l3);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mma_tf32(acc[j], l0, l1, l2, l3, bh[s][j][0], bh[s][j][1]);
+                    mma_tf32(acc[j], h0, h1, h2, h3, bl[s][j][0], bl[s][j][1]);
+                    mma_tf32(acc[j], h0, h1, h2, h3, bh[s][j][0], bh[s][j][1]);
+                }
+            } else {
+                orbits |= a0 | a1 | a2 | a3;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    mma_tf32(acc[j], a0, a1, a2, a3, bl[s][j][0], bl[s][j][1]);
+                    mma_tf32(acc[j], a0, a1, a2, a3, bh[s][j][0], bh[s][j][1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int z1 = z0 + g + 8 * h;
+            if (z1 < G1) {
+                float* o = y1 + (out_base + (int64_t)r * G1 + z1) * C1 + 2 * t;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float v0 = acc[j][2 * h], v1 = acc[j][2 * h + 1];
+                    *reinterpret_cast<float2*>(o + 8 * j) = make_float2(v0, v1);
+                    const float d0 = v0 - bias_r[j][0], d1 = v1 - bias_r[j][1];
+                    S1[j][0] += d0; S2[j][0] = fmaf(d0, d0, S2[j][0]);
+                    S1[j][1] += d1; S2[j][1] = fmaf(d1, d1, S2[j][1]);
+                }
+                cnt += 1.f;
+            }
+        }
+    }
+    return orbits & 0x1fffu;
+}
+
+__global__ void __launch_bounds__(C1M_THREADS)
+conv1_fwd_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
+                     const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y1,
+                     float* __restrict__ part, int G, int G1, int RBF, int total_rb, int rb_per_block) {
+    extern __shared__ __align__(128) float dsm[];
+    __shared__ float red[C1M_WARPS][3 * C1];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int P1 = G1 * G1 * G1, NYB = (G1 + RBF - 1) / RBF;
+    const int TL = (2 * RBF + 1) * G;
+    // B fragments: k slot q of k-step s <-> tap 8s + q (taps 27..31 are zero padding); n = g <-> channel 8j + g
+    uint32_t bh[4][2][2], bl[4][2][2];
+    int toff[4][2];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int tap = 8 * s + t + 4 * q, tc = min(tap, TAPS - 1);
+            toff[s][q] = (tc / 9) * TL + ((tc / 3) % 3) * G + tc % 3;          // slab i, row offset j, voxel offset l
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float wv = tap < TAPS ? w[(8 * j + g) * TAPS + tap] : 0.f;
+                bh[s][j][q] = to_tf32(wv);
+                bl[s][j][q] = to_tf32(wv - __uint_as_float(bh[s][j][q]));
+            }
+        }
+    float bias_r[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) bias_r[j][e] = bias[8 * j + 2 * t + e];
+    const int rb0 = blockIdx.x * rb_per_block, rb1 = min(total_rb, rb0 + rb_per_block);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto decode = [&](int rb, int& b, int& x1, int& y0, int& nr) {
+        b = rb / (G1 * NYB);
+        const int rem = rb - b * G1 * NYB;
+        x1 = rem / NYB;
+        y0 = (rem - x1 * NYB) * RBF;
+        nr = min(RBF, G1 - y0);
+    };
+    auto issue = [&](int rb, int stage) {
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * 3 * TL);
+        const uint32_t tri_bytes = (uint32_t)(2 * nr + 1) * G * 4;
+        mbar_expect_tx(bar, 3 * tri_bytes);
+        const float* orow = obs + (rows ? rows[b] : (int64_t)b) * obs_stride + grid_off;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+            bulk_g2s(dst + (uint32_t)(i * TL * 4), orow + ((int64_t)(2 * x1 + i) * G + 2 * y0) * G, tri_bytes, bar);
+    };
+    if (tid == 0 && rb0 < rb1) issue(rb0, 0);
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    for (int rb = rb0; rb < rb1; ++rb) {
+        const int stage = (rb - rb0) & 1;
+        if (tid == 0 && rb + 1 < rb1) issue(rb + 1, stage ^ 1);
+        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
+        phase[stage] ^= 1;
+        int b, x1, y0, nr;
+        decode(rb, b, x1, y0, nr);
+        const float* ts = dsm + stage * 3 * TL;
+        const int64_t out_base = (int64_t)b * P1 + ((int64_t)x1 * G1 + y0) * G1;
+        float S1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, S2[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, cnt = 0.f;
+        const uint32_t inexact = conv1_mma_rowblock<false>(ts, G, G1, nr, out_base, y1, bh, bl, toff, bias_r, S1, S2, cnt);
+        if (__syncthreads_or((int)inexact)) {                        // block-uniform: some input value is not a TF32 number
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) { S1[j][e] = 0.f; S2[j][e] = 0.f; }
+            cnt = 0.f;
+            conv1_mma_rowblock<true>(ts, G, G1, nr, out_base, y1, bh, bl, toff, bias_r, S1, S2, cnt);
+        }
+        if (part) {                                                  // uniform
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float n = cnt, mean = bias_r[j][e], M2 = 0.f;
+                    if (cnt > 0.f) {
+                        const float m = S1[j][e] / cnt;
+                        mean += m;
+                        M2 = fmaxf(S2[j][e] - S1[j][e] * m, 0.f);
+                    }
+#pragma unroll
+                    for (int o = 4; o < 32; o <<= 1) {               // lanes that share t hold the same channels
+                        const float nb = __shfl_xor_sync(0xffffffffu, n, o), mb = __shfl_xor_sync(0xffffffffu, mean, o),
+                                    qb = __shfl_xor_sync(0xffffffffu, M2, o);
+                        chan_merge_f(n, mean, M2, nb, mb, qb);
+                    }
+                    if (g == 0) {
+                        const int c = 8 * j + 2 * t + e;
+                        red[warp][c] = mean; red[warp][C1 + c] = M2; red[warp][2 * C1 + c] = n;
+                    }
+                }
+            __syncthreads();
+            if (tid < C1) {
+                float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll
+                for (int wv = 0; wv < C1M_WARPS; ++wv) chan_merge_f(n, mean, M2, red[wv][2 * C1 + tid], red[wv][tid], red[wv][C1 + tid]);
+                float* pr = part + (int64_t)rb * PART_STRIDE;
+                pr[tid] = mean; pr[C1 + tid] = M2;
+                if (tid == 0) pr[2 * C1] = n;
+            }
+        }
+        __syncthreads();                                             // stage and red[] are free for the next row block
+    }
+    if (!ok) { asm volatile("trap;"); }
+}
+
 // ---- two-level reductions of the per-block statistics (keeps the final single-block kernels short) -----------------
 constexpr int MERGE_FAN = 64;
 // forward BN partials (mean, M2, count) -> one record per MERGE_FAN input records (same layout)
@@ -1255,9 +1628,15 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     if (vec1f && smem_c1 <= 160 * 1024) {
         const int total_rb = B * d.nrb1;
         const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, 1184));
-        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c1));
-        conv1_fwd_tma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), CONV1_THREADS, smem_c1, stream>>>(
-            obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
+        if (conv1_mma_mode() & 1) {
+            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c1));
+            conv1_fwd_mma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), C1M_THREADS, smem_c1, stream>>>(
+                obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
+        } else {
+            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c1));
+            conv1_fwd_tma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), CONV1_THREADS, smem_c1, stream>>>(
+                obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
+        }
         nrec1 = total_rb;
     } else {
         conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
@@ -1429,6 +1808,12 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
         const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, w.nblk_wg1));
         const int nblk = (int)ceil_div(total_rb, rbpb);          // <= w.nblk_wg1: the partial buffer is large enough
         GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg1));
+        if (conv1_mma_mode() & 2) {
+            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg1));
+            conv1_wgrad_mma_kernel<<<nblk, C1M_THREADS, smem_wg1, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1,
+                                                                            ws + w.y1, ws + w.stat1, ws + w.coef1, ws + w.wg1part, d.G,
+                                                                            d.G1, total_rb, rbpb);
+        } else
         conv1_wgrad_tma_kernel<<<nblk, WG1_THREADS, smem_wg1, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1,
                                                                         ws + w.stat1, ws + w.coef1, ws + w.wg1part, d.G, d.G1,
                                                                         total_rb, rbpb);

@@ -4,8 +4,9 @@
 // unbounded) and at episode end reduces it with `torch.unique(torch.round(pts, decimals=2), dim=0)` to the distinct
 // 1 cm lattice points, sorted lexicographically.  torch.round(decimals=2) is nearbyint(x * 100.f) / 100.f in fp32, so a
 // point is identified by the integer triple k = nearbyint(p * 100); here every step appends the packed triple
-//     key = (kx + 2^20) << 42 | (ky + 2^20) << 21 | (kz + 2^20)
-// (8 B per point instead of 12, and ascending key order == the row order of torch.unique(dim=0)) to a per-env history
+//     key = (kx + 2^17) << 36 | (ky + 2^17) << 18 | (kz + 2^17)         (54 bits; |k| <= 2^17 - 1, i.e. +-1.31 km at 1 cm)
+// (8 B per point instead of 12, ascending key order == the row order of torch.unique(dim=0), and the 9 spare bits take an
+// env index so that ONE sort dedups the histories of up to 512 envs at episode end) to a per-env history
 // of capacity (max_episode_length + 1) * H * W, which cannot overflow.  At episode end the caller sorts / dedups the keys
 // and gnbv_keys_to_points turns them back into the fp32 rows k / 100.f the reference would hold.
 //
@@ -20,8 +21,10 @@
 namespace gnbv {
 
 constexpr int PTS_THREADS = 256;
-constexpr int KEY_BIAS = 1 << 20;
-constexpr float KEY_LIM = 1048575.0f;      // |k| <= 2^20 - 1 (10.48 km at 1 cm); the reference's depth clamp keeps |p| <~ 60 m
+constexpr int KEY_BITS = 18;
+constexpr int KEY_BIAS = 1 << (KEY_BITS - 1);
+constexpr int KEY_MASK = (1 << KEY_BITS) - 1;
+constexpr float KEY_LIM = 131071.0f;       // |k| <= 2^17 - 1 (1.31 km at 1 cm); the reference's depth clamp keeps |p| <~ 60 m
 
 __device__ __forceinline__ float depth_post_eval(float d) {     // env_train_base.py:520-523
     if (d != d) d = 0.0f;
@@ -39,7 +42,7 @@ __device__ __forceinline__ int64_t pack_key(float x, float y, float z) {
         float k = nearbyintf(__fmul_rn(p[a], 100.0f));          // round-half-even, as std::nearbyint on the CPU
         k = fminf(fmaxf(k, -KEY_LIM), KEY_LIM);
         if (k != k) k = 0.0f;
-        key = (key << 21) | (int64_t)((int)k + KEY_BIAS);
+        key = (key << KEY_BITS) | (int64_t)((int)k + KEY_BIAS);
     }
     return key;
 }
@@ -107,8 +110,9 @@ __global__ void keys_to_points_kernel(const int64_t* __restrict__ keys, int64_t 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int64_t key = keys[i];
-    const int kz = (int)(key & 0x1FFFFF) - KEY_BIAS, ky = (int)((key >> 21) & 0x1FFFFF) - KEY_BIAS,
-              kx = (int)((key >> 42) & 0x1FFFFF) - KEY_BIAS;
+    // bits above 3 * KEY_BITS (an env index added by the caller for batched dedup) are ignored
+    const int kz = (int)(key & KEY_MASK) - KEY_BIAS, ky = (int)((key >> KEY_BITS) & KEY_MASK) - KEY_BIAS,
+              kx = (int)((key >> (2 * KEY_BITS)) & KEY_MASK) - KEY_BIAS;
     pts[3 * i + 0] = __fdiv_rn((float)kx, 100.0f);
     pts[3 * i + 1] = __fdiv_rn((float)ky, 100.0f);
     pts[3 * i + 2] = __fdiv_rn((float)kz, 100.0f);

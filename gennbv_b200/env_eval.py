@@ -13,8 +13,9 @@ Differences from `Env_Train_GenNBV`, all taken from the reference class:
 
 B200-first: the history holds packed 8-byte lattice keys written by `scan_points_kernel` (one launch per step for all
 envs, capacity (max_episode_length + 1) * H * W per env, so it cannot overflow); at episode end the finished envs'
-keys are sorted / deduplicated (`torch.unique` on int64: plumbing), decoded by `keys_to_points_kernel`, and all finished
-envs go through ONE batched exact-1-NN chamfer launch group (`gennbv_b200.chamfer`, grid search for large clouds).
+keys are tagged with an env rank in their spare high bits and deduplicated by ONE sort (`torch.unique` on int64:
+plumbing), decoded by one `keys_to_points_kernel` launch, and all finished envs go through ONE batched exact-1-NN chamfer
+launch group (`gennbv_b200.chamfer`, grid search for large clouds).
 `pytorch3d.loss.chamfer_distance` is not vendored by the reference: parity of the accuracy value is unpinned
 (SURVEY.md 8c); the point history itself is pinned bit for bit by tests/golden/env_eval_*.npz.
 """
@@ -47,6 +48,7 @@ class Env_Eval_GenNBV(Env_Train_GenNBV):
         self._pts_count = torch.zeros(N, dtype=torch.int32, device=dev)
         self._pts_overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self._len_sum_before = None
+        self._gt_pack = None
 
     # ------------------------------------------------------------------ reference surface
     @property
@@ -105,6 +107,33 @@ class Env_Eval_GenNBV(Env_Train_GenNBV):
         c = int(self._pts_count[env_idx])
         return self._decode(torch.unique(self._pts_keys[env_idx, :c]))
 
+    ENV_KEY_SHIFT = 54                      # history keys use 54 bits (eval_points.cu); bits 54..62 carry an env rank
+    ENVS_PER_SORT = 512
+
+    def dedup_clouds(self, env_ids):
+        """`torch.unique(torch.round(pts_target_list[e], decimals=2), dim=0)` (:254-257) for many envs at once: the valid key
+        prefixes are tagged with the env's rank in the spare high bits and deduplicated by ONE sort (torch.unique on int64:
+        plumbing), then decoded by one kernel launch.  Returns (points [sum n, 3] f32 packed in env order, sizes list)."""
+        dev = self.device
+        pts_parts, sizes = [], []
+        for c0 in range(0, len(env_ids), self.ENVS_PER_SORT):
+            ids = env_ids[c0:c0 + self.ENVS_PER_SORT]
+            rows = torch.tensor(ids, device=dev)
+            cnt = self._pts_count[rows].long()
+            maxc = int(cnt.max())
+            if maxc == 0:
+                sizes += [0] * len(ids)
+                continue
+            keys = self._pts_keys[:, :maxc] if ids == list(range(self.num_envs)) else self._pts_keys[rows, :maxc]
+            rank = torch.arange(len(ids), device=dev, dtype=torch.int64)
+            valid = torch.arange(maxc, device=dev)[None, :] < cnt[:, None]
+            uniq = torch.unique((keys + (rank << self.ENV_KEY_SHIFT)[:, None])[valid])          # sorted: env rank major, key minor
+            bounds = torch.searchsorted(uniq, torch.arange(len(ids) + 1, device=dev, dtype=torch.int64) << self.ENV_KEY_SHIFT)
+            sizes += (bounds[1:] - bounds[:-1]).tolist()
+            pts_parts.append(self._decode(uniq))
+        pts = torch.cat(pts_parts, 0) if pts_parts else torch.zeros(0, 3, device=dev)
+        return pts, sizes
+
     def _before_reset_idx(self):
         """Accuracy of the envs that finish on this step (:250-264), then reset_idx's `pts_target_list[env] = empty`."""
         dones = self._dones_u8
@@ -116,12 +145,15 @@ class Env_Eval_GenNBV(Env_Train_GenNBV):
         if float(self._len_sum_before) > 0:
             todo = [e for e in done_ids if str(e) not in self.ratios_accuracy]
             if todo:
-                counts = self._pts_count[todo].tolist()
-                clouds = [self._decode(torch.unique(self._pts_keys[e, :c])) for e, c in zip(todo, counts)]
-                ok = [i for i, c in enumerate(counts) if c > 0]
+                pts, sizes = self.dedup_clouds(todo)
+                ok = [i for i, n in enumerate(sizes) if n > 0]
                 acc = [float("nan")] * len(todo)                 # an env that never saw the object has no scanned cloud
                 if ok:
-                    cx, cy = chamfer.chamfer_terms([clouds[i] for i in ok], [self.pc_gt[todo[i]] for i in ok])
+                    gt_key = tuple(todo[i] for i in ok)
+                    if self._gt_pack is None or self._gt_pack[0] != gt_key:     # GT clouds packed once per set of envs
+                        gts = [self.pc_gt[e] for e in gt_key]
+                        self._gt_pack = (gt_key, torch.cat(gts, 0).contiguous(), [int(g.shape[0]) for g in gts])
+                    cx, cy = chamfer.chamfer_terms_packed(pts, [sizes[i] for i in ok], self._gt_pack[1], self._gt_pack[2])
                     # `(chamfer_distance(...) * 100)[0]` (:258-259) repeats the returned tuple 100 times and takes its
                     # first element: the unscaled loss -- reproduced
                     for i, v in zip(ok, (cx + cy).tolist()):

@@ -318,7 +318,8 @@ int gnbv_gae(const float* rewards, const float* values, const uint8_t* episode_s
 /* ---- eval env: scanned-point history (gennbv/env/env_eval_gennbv.py:160-164, 253-257) ----
  * gnbv_scan_points: back_projection_fg (env_train_gennbv.py:494-526) for every foreground pixel (seg > 50), same fp32
  * chain as the voxelize path, appended to env n's history as the packed 1 cm lattice key
- *   key = (kx + 2^20) << 42 | (ky + 2^20) << 21 | (kz + 2^20),  k = nearbyint(p * 100.f)   (== torch.round(p, decimals=2) * 100)
+ *   key = (kx + 2^17) << 36 | (ky + 2^17) << 18 | (kz + 2^17),  k = nearbyint(p * 100.f)   (== torch.round(p, decimals=2) * 100),
+ *   |k| clamped to 2^17 - 1 (1.31 km); bits 54..62 are free for a caller-side env index (gnbv_keys_to_points ignores them)
  * keys [N, capacity] i64, counts [N] i32 in/out (number of keys held), overflow [1] i32 set to 1 if a history is full.
  * Ascending key order is the row order of torch.unique(dim=0) on the rounded points.  flags: GNBV_RAW_DEPTH as above.
  * gnbv_keys_to_points: keys [n] -> points [n,3] f32 = k / 100.f, the rows torch.round(decimals=2) produces. */

@@ -225,6 +225,157 @@ def wgrad(y1, sc, sh, dy2cl, G1, G2, B, nblocks):
     tot = rec.sum(0)
     return tot[:C * C * NT], tot[C * C * NT:]
 
+
+def conv1_fwd(x, w, bias, G, G1, B, RBF):
+    """conv1_fwd_mma_kernel: x [B,G,G,G] tri-class grid, w [16,27] -> y1 [B, G1^3, 16] channels-last (index logic only)."""
+    TAPS = 27
+    P1 = G1 ** 3
+    NYB = -(-G1 // RBF)
+    TL = (2 * RBF + 1) * G
+    y1 = np.full((B, P1, C), np.nan)
+    for rb in range(B * G1 * NYB):
+        b, rem = divmod(rb, G1 * NYB)
+        x1, yb = divmod(rem, NYB)
+        y0 = yb * RBF
+        nr = min(RBF, G1 - y0)
+        ts = np.zeros(3 * TL + 64)
+        for i in range(3):                     # the three TMA slabs: rows 2*y0 .. 2*y0 + 2*nr of plane 2*x1 + i
+            ts[i * TL:i * TL + (2 * nr + 1) * G] = x[b, 2 * x1 + i, 2 * y0:2 * y0 + 2 * nr + 1, :].reshape(-1)
+        out_base = (x1 * G1 + y0) * G1
+        ZT = (G1 + 15) // 16
+        for warp in range(8):
+            for tile in range(warp, nr * ZT, 8):
+                r, zt = divmod(tile, ZT)
+                z0 = 16 * zt
+                acc = np.zeros((2, 32, 4))
+                for lane in range(32):
+                    t = lane & 3
+                    for j in range(2):
+                        acc[j, lane, 0] = acc[j, lane, 2] = bias[8 * j + 2 * t]
+                        acc[j, lane, 1] = acc[j, lane, 3] = bias[8 * j + 2 * t + 1]
+                for s in range(4):
+                    a = []
+                    for lane in range(32):
+                        g, t = lane >> 2, lane & 3
+                        pa = (2 * r) * G + 2 * min(z0 + g, G1 - 1)
+                        pb = (2 * r) * G + 2 * min(z0 + g + 8, G1 - 1)
+                        toff = []
+                        for q in range(2):
+                            tc = min(8 * s + t + 4 * q, TAPS - 1)
+                            toff.append((tc // 9) * TL + ((tc // 3) % 3) * G + tc % 3)
+                        a.append((ts[pa + toff[0]], ts[pb + toff[0]], ts[pa + toff[1]], ts[pb + toff[1]]))
+                    for j in range(2):
+                        bfr = []
+                        for lane in range(32):
+                            g, t = lane >> 2, lane & 3
+                            vals = []
+                            for q in range(2):
+                                tap = 8 * s + t + 4 * q
+                                vals.append(w[(8 * j + g) * TAPS + tap] if tap < TAPS else 0.0)
+                            bfr.append(tuple(vals))
+                        mma(acc[j], a, bfr)
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    for h in range(2):
+                        z1 = z0 + g + 8 * h
+                        if z1 < G1:
+                            for j in range(2):
+                                for e in range(2):
+                                    idx = out_base + r * G1 + z1
+                                    assert np.isnan(y1[b, idx, 8 * j + 2 * t + e])
+                                    y1[b, idx, 8 * j + 2 * t + e] = acc[j, lane, 2 * h + e]
+    return y1
+
+
+def check_conv1(G, B=1):
+    G1 = (G - 3) // 2 + 1
+    RBF = max(1, min(G1, 256 // ((G1 + 3) // 4)))
+    x = torch.randint(-1, 2, (B, 1, G, G, G)).double()
+    wt = torch.randn(C, 1, 3, 3, 3, dtype=torch.float64)
+    bias = torch.randn(C, dtype=torch.float64)
+    ref = torch.nn.functional.conv3d(x, wt, bias, stride=2).permute(0, 2, 3, 4, 1).reshape(B, -1, C).numpy()
+    got = conv1_fwd(x[:, 0].numpy(), wt.numpy().reshape(-1), bias.numpy(), G, G1, B, RBF)
+    err = np.abs(got - ref).max()
+    print("G", G, "conv1 fwd max err", err, "unwritten", np.isnan(got).sum())
+    assert err < 1e-12 and not np.isnan(got).any()
+
+
+def conv1_wgrad(x, dy1, G, G1, B, nblocks=3):
+    """conv1_wgrad_mma_kernel index logic (BN1 backward omitted: dy1 given): x [B,G,G,G], dy1 [B,P1,16] -> dW [16*27], db [16]."""
+    TAPS, RB = 27, 16
+    P1 = G1 ** 3
+    NYB = -(-G1 // RB)
+    TL = (2 * RB + 1) * G
+    total_rb = B * G1 * NYB
+    rpb = -(-total_rb // nblocks)
+    rec = np.zeros((-(-total_rb // rpb), C * TAPS + C))
+    KS = (G1 + 7) // 8
+    for blk in range(rec.shape[0]):
+        acc = np.zeros((8, 4, 32, 4))
+        dbs = np.zeros((8, 32, 2))
+        for rb in range(blk * rpb, min(total_rb, blk * rpb + rpb)):
+            b, rem = divmod(rb, G1 * NYB)
+            x1, yb = divmod(rem, NYB)
+            y0 = yb * RB
+            nr = min(RB, G1 - y0)
+            ts = np.zeros(3 * TL + 64)
+            for i in range(3):
+                ts[i * TL:i * TL + (2 * nr + 1) * G] = x[b, 2 * x1 + i, 2 * y0:2 * y0 + 2 * nr + 1, :].reshape(-1)
+            gs = dy1[b, (x1 * G1 + y0) * G1:(x1 * G1 + y0 + nr) * G1].reshape(-1)
+            for warp in range(8):
+                for ks in range(warp, nr * KS, 8):
+                    r, kk = divmod(ks, KS)
+                    z0 = 8 * kk
+                    a, zz = [], []
+                    for lane in range(32):
+                        g, t = lane >> 2, lane & 3
+                        za, zb = z0 + t, z0 + t + 4
+                        zac, zbc = min(za, G1 - 1), min(zb, G1 - 1)
+                        av = []
+                        for q in range(4):
+                            h = q & 1
+                            zc, valid = (zbc, zb < G1) if (q >> 1) else (zac, za < G1)
+                            av.append(gs[(r * G1 + zc) * C + g + 8 * h] if valid else 0.0)
+                        dbs[warp, lane, 0] += av[0] + av[2]; dbs[warp, lane, 1] += av[1] + av[3]
+                        a.append(tuple(av)); zz.append((zac, zbc))
+                    for j in range(4):
+                        bfr = []
+                        for lane in range(32):
+                            g = lane >> 2
+                            tc = min(8 * j + g, TAPS - 1)
+                            boff = (tc // 9) * TL + ((tc // 3) % 3) * G + tc % 3
+                            zac, zbc = zz[lane]
+                            bfr.append((ts[(2 * r) * G + 2 * zac + boff], ts[(2 * r) * G + 2 * zbc + boff]))
+                        mma(acc[warp, j], a, bfr)
+        for warp in range(8):
+            for lane in range(32):
+                g, t = lane >> 2, lane & 3
+                for j in range(4):
+                    for e in range(4):
+                        co, tap = g + 8 * (e >> 1), 8 * j + 2 * t + (e & 1)
+                        if tap < TAPS:
+                            rec[blk, co * TAPS + tap] += acc[warp, j, lane, e]
+                if t == 0:
+                    rec[blk, C * TAPS + g] += sum(dbs[warp, 4 * g + tt, 0] for tt in range(4))
+                    rec[blk, C * TAPS + 8 + g] += sum(dbs[warp, 4 * g + tt, 1] for tt in range(4))
+    tot = rec.sum(0)
+    return tot[:C * TAPS], tot[C * TAPS:]
+
+
+def check_conv1_wgrad(G, B=1):
+    G1 = (G - 3) // 2 + 1
+    x = torch.randint(-1, 2, (B, 1, G, G, G)).double()
+    wt = torch.randn(C, 1, 3, 3, 3, dtype=torch.float64, requires_grad=True)
+    bias = torch.zeros(C, dtype=torch.float64, requires_grad=True)
+    out = torch.nn.functional.conv3d(x, wt, bias, stride=2)
+    dy = torch.randn_like(out)
+    (out * dy).sum().backward()
+    dy_cl = dy.permute(0, 2, 3, 4, 1).reshape(B, -1, C).numpy()
+    dW, db = conv1_wgrad(x[:, 0].numpy(), dy_cl, G, G1, B)
+    werr, berr = np.abs(dW - wt.grad.numpy().reshape(-1)).max(), np.abs(db - bias.grad.numpy()).max()
+    print("G", G, "conv1 wgrad max err", werr, "db err", berr)
+    assert werr < 1e-10 and berr < 1e-10
+
 def check(G1, B=1):
     G2 = (G1 - 3) // 2 + 1
     x = torch.randn(B, C, G1, G1, G1, dtype=torch.float64)           # pre-BN y1, NCDHW
@@ -260,3 +411,7 @@ def check(G1, B=1):
 if __name__ == "__main__":
     for G1 in ([int(a) for a in sys.argv[1:]] or [9, 10, 15]):
         check(G1, B=2 if G1 < 12 else 1)
+    check_conv1(20, B=2)
+    check_conv1(36, B=1)
+    check_conv1_wgrad(20, B=2)
+    check_conv1_wgrad(36, B=1)

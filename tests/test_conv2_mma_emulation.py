@@ -13,3 +13,5 @@ def test_fragment_mapping_reproduces_conv3d_and_its_data_gradient():
     spec.loader.exec_module(m)
     m.check(9, B=2)        # reference-native 20^3 grid: G1 = 9, G2 = 4 (partial tiles, every parity class)
     m.check(10, B=1)       # even G1: equal-sized parity classes, out-of-range odd taps
+    m.check_conv1(20, B=1)  # conv1 forward: slab offsets of the 32 k slots, two-row fragments, partial z tiles
+    m.check_conv1_wgrad(20, B=1)   # conv1 weight gradient: position k-steps, tap columns, per-warp partial records

@@ -99,6 +99,11 @@ def test_scanned_cloud_and_history_accessors():
         cloud = env.scanned_cloud(e)
         want = torch.unique(pts, dim=0)                      # history entries are already rounded
         assert torch.equal(cloud, want)
+    # batched dedup (one sort for several envs, any subset / order) == the per-env clouds
+    for ids in ([0, 1, 2], [2, 0], [1]):
+        pts, sizes = env.dedup_clouds(ids)
+        want = [env.scanned_cloud(e) for e in ids]
+        assert sizes == [int(w.shape[0]) for w in want] and torch.equal(pts, torch.cat(want, 0))
 
 
 def test_eval_wrapper_five_tuple_and_numpy_actions():

@@ -250,16 +250,34 @@ def test_tcgen05_conv2_path_is_parity_green(mode):
     assert out.returncode == 0 and "tc-conv2 ok" in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize("mode", ["0", "2", "6"])
-def test_every_conv2_kernel_variant_passes_the_encoder_parity_tests(mode):
-    """The default is GNBV_CONV2_TC=14 (mma.sync forward + data gradient + weight gradient, exercised by every other test in
-    this file).  Here the encoder forward/backward parity tests against torch autograd (all grid sizes, eval and training
-    BN) and the golden policy test are re-run in a subprocess with 0 (the CUDA-core kernels), 2 (mma.sync forward only)
-    and 6 (forward + data gradient), so that every kernel variant and every mix stays parity-green."""
+def test_encoder_forward_with_a_non_ternary_grid():
+    """The env only ever produces tri-class grids, but Hybrid_Encoder.forward takes any float observation: the tensor-core
+    conv1 kernel must notice inputs that are not exact in TF32 and take its split-operand path."""
+    G, B = 20, 6
+    pol, ref, D = make_policy(G, 11)
+    g = torch.Generator().manual_seed(11)
+    obs = torch.zeros(B, D)
+    obs[:, :600] = torch.randn(B, 600, generator=g)
+    obs[:, 600:600 + G ** 3] = torch.randn(B, G ** 3, generator=g) * 1.7 + 0.123
+    for training in (False, True):
+        ref.train(training); pol.train(training)
+        with torch.no_grad():
+            assert rel_err(pol.features_extractor(obs.to(DEV)).cpu(), ref.features_extractor(obs)) < RTOL
+
+
+@pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0"}, {"GNBV_CONV2_TC": "2"}, {"GNBV_CONV2_TC": "6"},
+                                 {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"}, {"GNBV_CONV1_MMA": "3"}],
+                         ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
+def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
+    """Defaults: GNBV_CONV2_TC=14 (mma.sync conv2 forward + data gradient + weight gradient) and the GNBV_CONV1_MMA default
+    of encoder.cu, exercised by every other test in this file.  Here the encoder forward/backward parity tests against
+    torch autograd (all grid sizes, eval and training BN), the non-ternary-grid test and the golden policy test are re-run
+    in a subprocess with the other settings -- CUDA-core conv2 kernels (0), partial mixes (2, 6), conv1 on CUDA cores (0) /
+    forward on tensor cores (1) / forward + weight gradient (3) -- so that every kernel variant stays parity-green."""
     import subprocess, sys
     here = os.path.abspath(__file__)
-    out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-k",
-                          "encoder_forward_backward_vs_torch or policy_matches_reference_golden_g20"],
-                         env={**os.environ, "GNBV_CONV2_TC": mode}, capture_output=True, text=True, timeout=900,
+    out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
+                          "encoder_forward_backward_vs_torch or policy_matches_reference_golden_g20 or non_ternary"],
+                         env={**os.environ, **env}, capture_output=True, text=True, timeout=900,
                          cwd=os.path.dirname(os.path.dirname(here)))
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
