@@ -42,9 +42,11 @@ static int conv2_tc_mode() {
     return mode;
 }
 
-// GNBV_CONV1_MMA: bit 1 = conv1 forward on the tensor cores (conv1_fwd_mma_kernel), bit 2 = conv1 weight gradient.
+// GNBV_CONV1_MMA: bit 1 = conv1 forward on the tensor cores (conv1_fwd_mma_kernel), bit 2 = conv1 weight gradient
+// (conv1_wgrad_mma_kernel).  Default 3: measured on B200 at B = 256, 64^3 (profiles/r01r): forward 0.434 -> 0.250 ms, weight
+// gradient 0.486 -> 0.433 ms against the CUDA-core TMA kernels (0), which stay available and tested.
 static int conv1_mma_mode() {
-    static const int mode = []() { const char* e = getenv("GNBV_CONV1_MMA"); return e ? atoi(e) : 0; }();
+    static const int mode = []() { const char* e = getenv("GNBV_CONV1_MMA"); return e ? atoi(e) : 3; }();
     return mode;
 }
 
