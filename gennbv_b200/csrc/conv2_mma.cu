@@ -128,37 +128,46 @@ conv2_fwd_mma_kernel(const float* __restrict__ y1, const float* __restrict__ sta
 #pragma unroll
             for (int j = 0; j < 2; ++j) { acc[m][j][0] = acc[m][j][2] = bias_r[j][0]; acc[m][j][1] = acc[m][j][3] = bias_r[j][1]; }
 
-        for (int ij = 0; ij < 9; ++ij) {
-            const int i = ij / 3, jy = ij - 3 * i;
-            const int tap_off = ((i * G1 + jy) * G1) * C;
+        // 27 taps, the loads of tap k+1 in flight while tap k is multiplied (two register buffers)
+        auto load = [&](float4 (&raw)[MT][2], int tap) {
+            const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
+            const int tap_off = ((i * G1 + jy) * G1 + l) * C;
 #pragma unroll
-            for (int l = 0; l < 3; ++l) {
-                const int tap = ij * 3 + l;
-                const float4* wt = wsm + tap * 128 + lane;
-                const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];       // ntile 0 hi/lo, ntile 1 hi/lo
-                const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
-                                           {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
-                const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
-                                           {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
-                float4 raw[MT][2];
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
-                for (int m = 0; m < MT; ++m)
+                for (int h = 0; h < 2; ++h) raw[m][h] = __ldg(reinterpret_cast<const float4*>(in_b + off[m][h] + tap_off));
+        };
+        auto compute = [&](const float4 (&raw)[MT][2], int tap) {
+            const float4* wt = wsm + tap * 128 + lane;
+            const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];       // ntile 0 hi/lo, ntile 1 hi/lo
+            const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
+                                       {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
+            const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
+                                       {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
 #pragma unroll
-                    for (int h = 0; h < 2; ++h)
-                        raw[m][h] = __ldg(reinterpret_cast<const float4*>(in_b + off[m][h] + tap_off + l * C));
+            for (int m = 0; m < MT; ++m) {
+                const Split4 r0 = bn_relu_split(raw[m][0], sc, sh), r1 = bn_relu_split(raw[m][1], sc, sh);
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const Split4 r0 = bn_relu_split(raw[m][0], sc, sh), r1 = bn_relu_split(raw[m][1], sc, sh);
+                for (int ks = 0; ks < 2; ++ks) {             // k-step A: channels (4t, 4t+1); k-step B: (4t+2, 4t+3)
+                    const int e0 = 2 * ks, e1 = 2 * ks + 1;
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {             // k-step A: channels (4t, 4t+1); k-step B: (4t+2, 4t+3)
-                        const int e0 = 2 * ks, e1 = 2 * ks + 1;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
-                            mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
-                            mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
-                        }
+                    for (int j = 0; j < 2; ++j) {
+                        mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
+                        mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
+                        mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
                     }
+                }
+            }
+        };
+        {
+            float4 raw_a[MT][2], raw_b[MT][2];
+            load(raw_a, 0);
+            for (int tap = 0; tap < NTAPS; tap += 2) {
+                if (tap + 1 < NTAPS) load(raw_b, tap + 1);
+                compute(raw_a, tap);
+                if (tap + 1 < NTAPS) {
+                    if (tap + 2 < NTAPS) load(raw_a, tap + 2);
+                    compute(raw_b, tap + 1);
                 }
             }
         }
@@ -282,15 +291,6 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
         }
         wsm[idx] = make_float4(v[0], v[1], v[2], v[3]);
     }
-    // BN1 constants of the thread's 4 output channels c = 8j + 2t + e
-    float k_mean[2][2], k_istd[2][2], k_a[2][2], k_b[2][2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int c = 8 * j + 2 * t + e;
-            k_mean[j][e] = stat1[c]; k_istd[j][e] = stat1[C + c]; k_a[j][e] = stat1[2 * C + c]; k_b[j][e] = stat1[3 * C + c];
-        }
     __syncthreads();
 
     const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
@@ -335,48 +335,78 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
                 for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.f;
         const float* dy_b = dy2cl + (int64_t)b * P2 * C + 4 * t;
 
-        // taps of the class: per axis, parity 0 -> kernel offsets {0, 2} (source shift 0, 1); parity 1 -> {1} (shift 0)
+        // taps of the class: per axis, parity 0 -> kernel offsets {0, 2} (source shift 0, 1); parity 1 -> {1} (shift 0).
+        // The 1 / 2 / 4 / 8 taps are walked with the loads of tap k+1 in flight while tap k is multiplied (two register
+        // buffers): the A rows come straight from L2 / HBM and their latency is what this kernel has to hide.
         const int nix = cl.cx ? 1 : 2, niy = cl.cy ? 1 : 2, niz = cl.cz ? 1 : 2;
-        for (int ax = 0; ax < nix; ++ax)
-            for (int ay = 0; ay < niy; ++ay)
-                for (int az = 0; az < niz; ++az) {
-                    const int i = cl.cx ? 1 : 2 * ax, jy = cl.cy ? 1 : 2 * ay, l = cl.cz ? 1 : 2 * az;
-                    const int tap = (i * 3 + jy) * 3 + l;
-                    const int delta = ((ax * G2 + ay) * G2 + az) * C;           // source shift (i>>1, j>>1, l>>1) = (ax, ay, az)
-                    const uint32_t need = (1u << ax) | (4u << ay) | (16u << az);
-                    const float4* wt = wsm + tap * 128 + lane;
-                    const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];
-                    const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
-                                               {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
-                    const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
-                                               {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
-                    float4 raw[MT][2];
+        const int ntap = nix * niy * niz;
+        auto tap_of = [&](int k, int& tap, int& delta, uint32_t& need) {
+            const int az = niz == 2 ? (k & 1) : 0, k2 = niz == 2 ? (k >> 1) : k;
+            const int ay = niy == 2 ? (k2 & 1) : 0, ax = niy == 2 ? (k2 >> 1) : k2;
+            const int i = cl.cx ? 1 : 2 * ax, jy = cl.cy ? 1 : 2 * ay, l = cl.cz ? 1 : 2 * az;
+            tap = (i * 3 + jy) * 3 + l;
+            delta = ((ax * G2 + ay) * G2 + az) * C;               // source shift (i>>1, j>>1, l>>1) = (ax, ay, az)
+            need = (1u << ax) | (4u << ay) | (16u << az);
+        };
+        auto load = [&](float4 (&raw)[MT][2], int delta, uint32_t need) {
 #pragma unroll
-                    for (int m = 0; m < MT; ++m)
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
-                        for (int h = 0; h < 2; ++h)
-                            raw[m][h] = (okb[m][h] & need) == need
-                                            ? __ldg(reinterpret_cast<const float4*>(dy_b + src[m][h] - delta))
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int h = 0; h < 2; ++h)
+                    raw[m][h] = (okb[m][h] & need) == need ? __ldg(reinterpret_cast<const float4*>(dy_b + src[m][h] - delta))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto compute = [&](const float4 (&raw)[MT][2], int tap) {
+            const float4* wt = wsm + tap * 128 + lane;
+            const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];
+            const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
+                                       {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
+            const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
+                                       {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const Split4 r0 = split4(raw[m][0]), r1 = split4(raw[m][1]);
+            for (int m = 0; m < MT; ++m) {
+                const Split4 r0 = split4(raw[m][0]), r1 = split4(raw[m][1]);
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
-                            const int e0 = 2 * ks, e1 = 2 * ks + 1;
+                for (int ks = 0; ks < 2; ++ks) {
+                    const int e0 = 2 * ks, e1 = 2 * ks + 1;
 #pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
-                                mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
-                                mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
-                            }
-                        }
+                    for (int j = 0; j < 2; ++j) {
+                        mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
+                        mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
+                        mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
                     }
                 }
+            }
+        };
+        {
+            float4 raw_a[MT][2], raw_b[MT][2];
+            int tap0, d0, tap1 = 0, d1 = 0;
+            uint32_t n0, n1 = 0;
+            tap_of(0, tap0, d0, n0);
+            load(raw_a, d0, n0);
+            for (int k = 0; k < ntap; k += 2) {                   // all conditions are block-uniform
+                const bool has1 = k + 1 < ntap;
+                if (has1) { tap_of(k + 1, tap1, d1, n1); load(raw_b, d1, n1); }
+                compute(raw_a, tap0);
+                if (has1) {
+                    if (k + 2 < ntap) { tap_of(k + 2, tap0, d0, n0); load(raw_a, d0, n0); }
+                    compute(raw_b, tap1);
+                }
+            }
+        }
 
         // ---- epilogue: ReLU mask from bn1(y1), store g1 (channels-last), BN1-backward partial sums.
         // All 16 y1 loads of the thread are issued before the first use: one exposed memory latency instead of eight.
         float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+        float k_mean[2][2], k_istd[2][2], k_a[2][2], k_b[2][2];     // BN1 constants of the thread's channels c = 8j + 2t + e
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * j + 2 * t + e;
+                k_mean[j][e] = __ldg(stat1 + c); k_istd[j][e] = __ldg(stat1 + C + c);
+                k_a[j][e] = __ldg(stat1 + 2 * C + c); k_b[j][e] = __ldg(stat1 + 3 * C + c);
+            }
         float2 yv[MT][2][2];
 #pragma unroll
         for (int m = 0; m < MT; ++m)

@@ -1077,7 +1077,10 @@ conv1_fwd_tma_kernel(const float* __restrict__ obs, int64_t obs_stride, const in
 // staged y-row.  A = dy1^T is formed in registers from the staged g1 / y1 rows (BN1 backward on the fly) and split hi/lo;
 // B = the tri-class input, exact in TF32 (checked like the forward kernel: a row block whose inputs are not TF32 numbers is
 // redone with B split too).  The 8 warps of a block take different k-steps and their 16-register accumulators are
-// combined through shared memory at the end, exactly like the CUDA-core kernel's record.
+// combined through shared memory at the end, exactly like the CUDA-core kernel's record.  Row blocks are RB = 8 output rows
+// (45 KB per stage at 64^3) so that two blocks fit an SM: the kernel is a streaming reduction (1.25 GB in, 7 KB out per
+// block) and needs copies in flight more than it needs large tiles.
+constexpr int WG1M_RB = 8;
 constexpr int C1M_THREADS = 256;
 constexpr int C1M_WARPS = C1M_THREADS / 32;
 
@@ -1132,7 +1135,8 @@ __device__ __forceinline__ uint32_t conv1_wgrad_mma_rowblock(const float* __rest
     return orbits & 0x1fffu;
 }
 
-__global__ void __launch_bounds__(C1M_THREADS)
+template <int RB>
+__global__ void __launch_bounds__(C1M_THREADS, 2)
 conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
                        const float* __restrict__ g1, const float* __restrict__ y1, const float* __restrict__ stat1,
                        const float* __restrict__ coef, float* __restrict__ part, int G, int G1, int total_rb, int rb_per_block) {
@@ -1140,9 +1144,9 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
     __shared__ float red[C1M_WARPS][WG1_REC];
     __shared__ __align__(8) uint64_t mbar[2];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-    const int P1 = G1 * G1 * G1, NYB = (G1 + WG1_RB - 1) / WG1_RB;
-    const int TL = (2 * WG1_RB + 1) * G;                    // floats per staged tri slab
-    const int GL = WG1_RB * G1 * C1;                        // floats per staged g1 / y1 slab
+    const int P1 = G1 * G1 * G1, NYB = (G1 + RB - 1) / RB;
+    const int TL = (2 * RB + 1) * G;                    // floats per staged tri slab
+    const int GL = RB * G1 * C1;                        // floats per staged g1 / y1 slab
     const int STAGE = 3 * TL + 2 * GL;
     float acc[4][4];
 #pragma unroll
@@ -1171,8 +1175,8 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
         b = rb / (G1 * NYB);
         const int rem = rb - b * G1 * NYB;
         x1 = rem / NYB;
-        y0 = (rem - x1 * NYB) * WG1_RB;
-        nr = min(WG1_RB, G1 - y0);
+        y0 = (rem - x1 * NYB) * RB;
+        nr = min(RB, G1 - y0);
     };
     auto issue = [&](int rb, int stage) {                   // thread 0 only
         int b, x1, y0, nr;
@@ -1808,13 +1812,18 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     if (vec1 && smem_wg1 <= 190 * 1024) {
         const int nyb = (int)ceil_div(d.G1, WG1_RB), total_rb = B * d.G1 * nyb;
         const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, w.nblk_wg1));
-        const int nblk = (int)ceil_div(total_rb, rbpb);          // <= w.nblk_wg1: the partial buffer is large enough
+        int nblk = (int)ceil_div(total_rb, rbpb);                // <= w.nblk_wg1: the partial buffer is large enough
         GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg1));
         if (conv1_mma_mode() & 2) {
-            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg1));
-            conv1_wgrad_mma_kernel<<<nblk, C1M_THREADS, smem_wg1, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1,
-                                                                            ws + w.y1, ws + w.stat1, ws + w.coef1, ws + w.wg1part, d.G,
-                                                                            d.G1, total_rb, rbpb);
+            const int nyb_m = (int)ceil_div(d.G1, WG1M_RB), total_m = B * d.G1 * nyb_m;
+            const int rbpb_m = (int)std::max<int64_t>(1, ceil_div(total_m, w.nblk_wg1));
+            const int nblk_m = (int)ceil_div(total_m, rbpb_m);
+            const size_t smem_m = (size_t)2 * (3 * (2 * WG1M_RB + 1) * d.G + 2 * WG1M_RB * d.G1 * C1) * 4;
+            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_mma_kernel<WG1M_RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+            conv1_wgrad_mma_kernel<WG1M_RB><<<nblk_m, C1M_THREADS, smem_m, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1,
+                                                                                     ws + w.y1, ws + w.stat1, ws + w.coef1, ws + w.wg1part,
+                                                                                     d.G, d.G1, total_m, rbpb_m);
+            nblk = nblk_m;
         } else
         conv1_wgrad_tma_kernel<<<nblk, WG1_THREADS, smem_wg1, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1,
                                                                         ws + w.stat1, ws + w.coef1, ws + w.wg1part, d.G, d.G1,

@@ -302,7 +302,7 @@ def check_conv1(G, B=1):
 
 def conv1_wgrad(x, dy1, G, G1, B, nblocks=3):
     """conv1_wgrad_mma_kernel index logic (BN1 backward omitted: dy1 given): x [B,G,G,G], dy1 [B,P1,16] -> dW [16*27], db [16]."""
-    TAPS, RB = 27, 16
+    TAPS, RB = 27, 8
     P1 = G1 ** 3
     NYB = -(-G1 // RB)
     TL = (2 * RB + 1) * G
