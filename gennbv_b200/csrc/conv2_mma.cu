@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv2_mma.cuh"
 #include "mma.cuh"
+#include "tma.cuh"
 
 #include <algorithm>
 
@@ -128,46 +129,39 @@ conv2_fwd_mma_kernel(const float* __restrict__ y1, const float* __restrict__ sta
 #pragma unroll
             for (int j = 0; j < 2; ++j) { acc[m][j][0] = acc[m][j][2] = bias_r[j][0]; acc[m][j][1] = acc[m][j][3] = bias_r[j][1]; }
 
-        // 27 taps, the loads of tap k+1 in flight while tap k is multiplied (two register buffers)
-        auto load = [&](float4 (&raw)[MT][2], int tap) {
-            const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
-            const int tap_off = ((i * G1 + jy) * G1 + l) * C;
+        // (explicit register double-buffering of the tap loads was measured slower here: 0.291 vs 0.275 ms -- the unrolled
+        // l loop already keeps three taps of loads in flight and the extra index arithmetic costs more than it hides)
+        for (int ij = 0; ij < 9; ++ij) {
+            const int i = ij / 3, jy = ij - 3 * i;
+            const int tap_off = ((i * G1 + jy) * G1) * C;
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
+            for (int l = 0; l < 3; ++l) {
+                const int tap = ij * 3 + l;
+                const float4* wt = wsm + tap * 128 + lane;
+                const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];       // ntile 0 hi/lo, ntile 1 hi/lo
+                const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
+                                           {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
+                const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
+                                           {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
+                float4 raw[MT][2];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) raw[m][h] = __ldg(reinterpret_cast<const float4*>(in_b + off[m][h] + tap_off));
-        };
-        auto compute = [&](const float4 (&raw)[MT][2], int tap) {
-            const float4* wt = wsm + tap * 128 + lane;
-            const float4 w0h = wt[0], w0l = wt[32], w1h = wt[64], w1l = wt[96];       // ntile 0 hi/lo, ntile 1 hi/lo
-            const uint32_t bh[2][4] = {{__float_as_uint(w0h.x), __float_as_uint(w0h.y), __float_as_uint(w0h.z), __float_as_uint(w0h.w)},
-                                       {__float_as_uint(w1h.x), __float_as_uint(w1h.y), __float_as_uint(w1h.z), __float_as_uint(w1h.w)}};
-            const uint32_t bl[2][4] = {{__float_as_uint(w0l.x), __float_as_uint(w0l.y), __float_as_uint(w0l.z), __float_as_uint(w0l.w)},
-                                       {__float_as_uint(w1l.x), __float_as_uint(w1l.y), __float_as_uint(w1l.z), __float_as_uint(w1l.w)}};
+                for (int m = 0; m < MT; ++m)
 #pragma unroll
-            for (int m = 0; m < MT; ++m) {
-                const Split4 r0 = bn_relu_split(raw[m][0], sc, sh), r1 = bn_relu_split(raw[m][1], sc, sh);
+                    for (int h = 0; h < 2; ++h)
+                        raw[m][h] = __ldg(reinterpret_cast<const float4*>(in_b + off[m][h] + tap_off + l * C));
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {             // k-step A: channels (4t, 4t+1); k-step B: (4t+2, 4t+3)
-                    const int e0 = 2 * ks, e1 = 2 * ks + 1;
+                for (int m = 0; m < MT; ++m) {
+                    const Split4 r0 = bn_relu_split(raw[m][0], sc, sh), r1 = bn_relu_split(raw[m][1], sc, sh);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
-                        mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
-                        mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
+                    for (int ks = 0; ks < 2; ++ks) {             // k-step A: channels (4t, 4t+1); k-step B: (4t+2, 4t+3)
+                        const int e0 = 2 * ks, e1 = 2 * ks + 1;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            mma_tf32(acc[m][j], r0.lo[e0], r1.lo[e0], r0.lo[e1], r1.lo[e1], bh[j][e0], bh[j][e1]);
+                            mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bl[j][e0], bl[j][e1]);
+                            mma_tf32(acc[m][j], r0.hi[e0], r1.hi[e0], r0.hi[e1], r1.hi[e1], bh[j][e0], bh[j][e1]);
+                        }
                     }
-                }
-            }
-        };
-        {
-            float4 raw_a[MT][2], raw_b[MT][2];
-            load(raw_a, 0);
-            for (int tap = 0; tap < NTAPS; tap += 2) {
-                if (tap + 1 < NTAPS) load(raw_b, tap + 1);
-                compute(raw_a, tap);
-                if (tap + 1 < NTAPS) {
-                    if (tap + 2 < NTAPS) load(raw_a, tap + 2);
-                    compute(raw_b, tap + 1);
                 }
             }
         }
@@ -305,27 +299,34 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
         }
         const int row0 = r * ROWS_PER_ITEM + warp * ROWS_PER_WARP;
         const float inv_nz = 1.0f / (float)cl.nz, inv_ny = 1.0f / (float)cl.ny;
-        // per row: dy2 offset of the (di,dj,dl) = (0,0,0) source voxel, output voxel index, validity bits
+        // per row: dy2 offset of the (di,dj,dl) = (0,0,0) source voxel, output voxel index, validity bits.
+        // The thread's rows are v0, v0 + 8, v0 + 16, ...: the first one is decoded by division, the others by stepping the
+        // (xi, yi, zi) counter 8 voxels forward with carries.
         int src[MT][2], dst[MT][2];
         uint32_t okb[MT][2];
+        {
+            const int v0 = row0 + g;
+            const int q0 = fast_div(v0, inv_nz);
+            int zi = v0 - q0 * cl.nz, xi = fast_div(q0, inv_ny), yi = q0 - xi * cl.ny;
 #pragma unroll
-        for (int m = 0; m < MT; ++m)
+            for (int m = 0; m < MT; ++m)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int v = row0 + m * 16 + g + 8 * h;
-                const bool in = v < cl.nvox;
-                const int vv = in ? v : 0;
-                const int q = fast_div(vv, inv_nz), zi = vv - q * cl.nz, xi = fast_div(q, inv_ny), yi = q - xi * cl.ny;
-                src[m][h] = ((xi * G2 + yi) * G2 + zi) * C;
-                dst[m][h] = in ? ((2 * xi + cl.cx) * G1 + (2 * yi + cl.cy)) * G1 + (2 * zi + cl.cz) : -1;
-                // bit 2a: source index (coordinate - 0) < G2;  bit 2a+1: (coordinate - 1) >= 0
-                uint32_t bits = 0;
-                if (in) {
-                    bits = (xi < G2 ? 1u : 0u) | (xi >= 1 ? 2u : 0u) | (yi < G2 ? 4u : 0u) | (yi >= 1 ? 8u : 0u) |
-                           (zi < G2 ? 16u : 0u) | (zi >= 1 ? 32u : 0u);
+                for (int h = 0; h < 2; ++h) {
+                    const bool in = row0 + m * 16 + g + 8 * h < cl.nvox;
+                    src[m][h] = in ? ((xi * G2 + yi) * G2 + zi) * C : 0;
+                    dst[m][h] = in ? ((2 * xi + cl.cx) * G1 + (2 * yi + cl.cy)) * G1 + (2 * zi + cl.cz) : -1;
+                    // bit 2a: source index (coordinate - 0) < G2;  bit 2a+1: (coordinate - 1) >= 0
+                    uint32_t bits = 0;
+                    if (in) {
+                        bits = (xi < G2 ? 1u : 0u) | (xi >= 1 ? 2u : 0u) | (yi < G2 ? 4u : 0u) | (yi >= 1 ? 8u : 0u) |
+                               (zi < G2 ? 16u : 0u) | (zi >= 1 ? 32u : 0u);
+                    }
+                    okb[m][h] = bits;
+                    zi += 8;
+                    while (zi >= cl.nz) { zi -= cl.nz; ++yi; }
+                    while (yi >= cl.ny) { yi -= cl.ny; ++xi; }
                 }
-                okb[m][h] = bits;
-            }
+        }
         float acc[MT][2][4];
 #pragma unroll
         for (int m = 0; m < MT; ++m)
@@ -547,6 +548,139 @@ conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ s
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// conv2 weight gradient, staged version (same contract as conv2_wgrad_mma_kernel, default).  The register-path kernel
+// above is latency-bound on its scalar global loads (tensor pipe 26 % busy).  Here a block of 8 warps walks GROUPS of
+// four consecutive output rows (b, x2, y2 = 4Yg .. 4Yg+3): the 27 input lines (3 x-planes x 9 y-lines of G1 voxels x 16
+// channels) and the 4 dy2 lines of a group are fetched by TMA bulk copies into a double-buffered shared-memory stage while
+// the previous group is multiplied.  A k-step = 4 rows x 2 adjacent z positions: fragment slot t <-> (row t, z), slot
+// t+4 <-> (row t, z+1).  With that choice the four t-lanes of a fragment load read four DIFFERENT staged lines, and the
+// line pitch is padded to 4 (mod 32) floats (dy2 lines: 8 mod 32), so the 32 lanes of every LDS hit 32 different banks
+// -- positions of one line alone are always 32 floats apart and would collide four ways.
+// The 54 n-tiles (27 taps x 2 channel halves) are dealt round-robin to the 8 warps (<= 7 each = 28 accumulators).
+constexpr int WGS_THREADS = 256;
+constexpr int WGS_WARPS = WGS_THREADS / 32;
+constexpr int WGS_NT = (2 * NTAPS + WGS_WARPS - 1) / WGS_WARPS;      // 7 n-tiles per warp
+constexpr int WGS_ROWS = 4;
+
+__host__ __device__ inline int pad_mod32(int n, int r) {             // smallest multiple-of-4 value >= n that is r (mod 32)
+    int v = (n / 32) * 32 + r;
+    return v >= n ? v : v + 32;
+}
+
+__global__ void __launch_bounds__(WGS_THREADS, 1)
+conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
+                          float* __restrict__ part, int G1, int G2, int total_groups, int groups_per_block) {
+    extern __shared__ __align__(128) float dsm[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
+    const int LP = pad_mod32(G1 * C, 4), DP = pad_mod32(G2 * C, 8);         // floats per staged y1 / dy2 line
+    const int STAGE = 27 * LP + WGS_ROWS * DP;
+    const int NYG = (G2 + WGS_ROWS - 1) / WGS_ROWS;
+    const uint32_t line_bytes = (uint32_t)G1 * C * 4, dy_bytes = (uint32_t)G2 * C * 4;
+    // BN1 scale / shift of the two input channels this lane supplies as B columns: ci = 8*hf + g
+    // (n-tile nt = warp + 8k <-> tap nt >> 1, channel half nt & 1 = warp & 1: a warp only ever sees one channel half)
+    const int hf = warp & 1;
+    const float scv = stat1[2 * C + 8 * hf + g], shv = stat1[3 * C + 8 * hf + g];
+    float acc[WGS_NT][4];
+#pragma unroll
+    for (int k = 0; k < WGS_NT; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+    float db_lo = 0.f, db_hi = 0.f;
+    const int g0 = blockIdx.x * groups_per_block, g1 = min(total_groups, g0 + groups_per_block);
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init_fence(); }
+    __syncthreads();
+    auto decode = [&](int grp, int& b, int& x2, int& y20, int& nrows) {
+        b = grp / (G2 * NYG);
+        const int rem = grp - b * G2 * NYG;
+        x2 = rem / NYG;
+        y20 = (rem - x2 * NYG) * WGS_ROWS;
+        nrows = min(WGS_ROWS, G2 - y20);
+    };
+    auto issue = [&](int grp, int stage) {                  // thread 0 only
+        int b, x2, y20, nrows;
+        decode(grp, b, x2, y20, nrows);
+        const int nlines = 2 * nrows + 1;                   // input y-lines 2*y20 .. 2*y20 + 2*nrows
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * STAGE);
+        mbar_expect_tx(bar, 3 * nlines * line_bytes + nrows * dy_bytes);
+        for (int i = 0; i < 3; ++i)
+            for (int yl = 0; yl < nlines; ++yl)
+                bulk_g2s(dst + (uint32_t)((i * 9 + yl) * LP * 4),
+                         y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2 + i) * G1 + (2 * y20 + yl)) * G1) * C, line_bytes, bar);
+        for (int r = 0; r < nrows; ++r)
+            bulk_g2s(dst + (uint32_t)((27 * LP + r * DP) * 4), dy2cl + ((int64_t)b * P2 + (int64_t)(x2 * G2 + y20 + r) * G2) * C,
+                     dy_bytes, bar);
+    };
+    if (tid == 0 && g0 < g1) issue(g0, 0);
+    uint32_t phase[2] = {0, 0};
+    bool ok = true;
+    const int nzp = (G2 + 1) / 2;
+    for (int grp = g0; grp < g1; ++grp) {
+        const int stage = (grp - g0) & 1;
+        if (tid == 0 && grp + 1 < g1) issue(grp + 1, stage ^ 1);     // stage^1 was released by the barrier ending grp-1
+        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
+        phase[stage] ^= 1;
+        int b, x2, y20, nrows;
+        decode(grp, b, x2, y20, nrows);
+        const float* xs = dsm + stage * STAGE;
+        const float* dys = xs + 27 * LP;
+        const bool vrow = t < nrows;
+        const int tc = min(t, nrows - 1);                   // rows past the grid alias the last valid row (their A is 0)
+        for (int zp = 0; zp < nzp; ++zp) {
+            const int za = 2 * zp, zb = za + 1;
+            const bool vb = zb < G2;
+            const int zbc = min(zb, G2 - 1);
+            // A = dy2^T: a0 (co g, row t, z za), a1 (co g+8, ...), a2 (co g, row t, z zb), a3 (co g+8, ...)
+            const float* da = dys + tc * DP + za * C + g;
+            const float* db = dys + tc * DP + zbc * C + g;
+            const float a0 = vrow ? da[0] : 0.f, a1 = vrow ? da[8] : 0.f;
+            const float a2 = (vrow && vb) ? db[0] : 0.f, a3 = (vrow && vb) ? db[8] : 0.f;
+            if (warp == 0) { db_lo += a0 + a2; db_hi += a1 + a3; }
+            uint32_t ah[4], al[4];
+            split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]); split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+#pragma unroll
+            for (int k = 0; k < WGS_NT; ++k) {
+                const int nt = warp + WGS_WARPS * k;
+                if (nt < 2 * NTAPS) {                       // warp-uniform
+                    const int tap = nt >> 1;
+                    const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
+                    // B (k = position, n = ci): b0 = x[row t, 2*za + l][ci], b1 = x[row t, 2*zb + l][ci]
+                    const float* line = xs + (i * 9 + 2 * tc + jy) * LP + l * C + 8 * hf + g;
+                    const float x0 = fmaxf(fmaf(scv, line[2 * za * C], shv), 0.f);
+                    const float x1 = fmaxf(fmaf(scv, line[2 * zbc * C], shv), 0.f);
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(x0, bh0, bl0); split_tf32(x1, bh1, bl1);
+                    mma_tf32(acc[k], al[0], al[1], al[2], al[3], bh0, bh1);
+                    mma_tf32(acc[k], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+                    mma_tf32(acc[k], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
+                }
+            }
+        }
+        __syncthreads();                                    // everyone is done with this stage before it is refilled
+    }
+    if (!ok) { asm volatile("trap;"); }
+    float* out = part + (int64_t)blockIdx.x * WG_REC;
+#pragma unroll
+    for (int k = 0; k < WGS_NT; ++k) {
+        const int nt = warp + WGS_WARPS * k;
+        if (nt < 2 * NTAPS) {
+            const int tap = nt >> 1;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int co = g + 8 * (e >> 1), ci = 8 * hf + 2 * t + (e & 1);
+                out[(co * C + ci) * NTAPS + tap] = acc[k][e];
+            }
+        }
+    }
+    if (warp == 0) {
+        db_lo += __shfl_xor_sync(0xffffffffu, db_lo, 1); db_lo += __shfl_xor_sync(0xffffffffu, db_lo, 2);
+        db_hi += __shfl_xor_sync(0xffffffffu, db_hi, 1); db_hi += __shfl_xor_sync(0xffffffffu, db_hi, 2);
+        if (t == 0) { out[C * C * NTAPS + g] = db_lo; out[C * C * NTAPS + 8 + g] = db_hi; }
+    }
+}
+
 }  // namespace
 
 int conv2_mma_chunks(int G2) { return (int)ceil_div((int64_t)G2 * G2 * G2, ROWS_PER_ITEM); }
@@ -590,6 +724,25 @@ int launch_conv2_wgrad_mma(const float* y1, const float* stat1, const float* dy2
                            int nblocks, int rows_per_block, cudaStream_t stream) {
     conv2_wgrad_mma_kernel<<<nblocks, MMA_THREADS, 0, stream>>>(y1, stat1, dy2cl, part, G1, G2, B * G2 * G2, rows_per_block);
     GNBV_LAUNCH_CHECK("conv2_wgrad_mma_kernel");
+    return GNBV_OK;
+}
+
+int launch_conv2_wgrad_staged(const float* y1, const float* stat1, const float* dy2cl, float* part, int B, int G1, int G2,
+                              int max_blocks, int* nblocks_out, cudaStream_t stream) {
+    const int LP = pad_mod32(G1 * C, 4), DP = pad_mod32(G2 * C, 8);
+    const size_t smem = (size_t)2 * (27 * LP + WGS_ROWS * DP) * 4;
+    GNBV_REQUIRE(smem <= 200 * 1024, "conv2 wgrad: grid too large for the staged kernel's shared-memory lines");
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int total = B * G2 * (int)ceil_div(G2, WGS_ROWS);
+    const int want = std::min(std::min(max_blocks, 148), total);
+    const int gpb = (int)ceil_div(total, want), nblk = (int)ceil_div(total, gpb);
+    conv2_wgrad_staged_kernel<<<nblk, WGS_THREADS, smem, stream>>>(y1, stat1, dy2cl, part, G1, G2, total, gpb);
+    GNBV_LAUNCH_CHECK("conv2_wgrad_staged_kernel");
+    *nblocks_out = nblk;
     return GNBV_OK;
 }
 

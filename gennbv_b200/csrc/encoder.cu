@@ -17,6 +17,7 @@
 #include "conv2_tc.cuh"
 #include "conv2_mma.cuh"
 #include "mma.cuh"
+#include "tma.cuh"
 
 #include <stdlib.h>
 
@@ -422,23 +423,6 @@ constexpr int WG2_THREADS = 256;
 constexpr int WG2_TT = 7;
 constexpr int WG2_MAX_BLOCKS = 592;
 constexpr int WG2_REC = C1 * C1 * TAPS + C1;
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(mbar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_wait_parity(uint32_t mbar, uint32_t parity) {
-    for (uint32_t it = 0; it < (1u << 26); ++it) {          // bounded: a lost copy must not hang the GPU
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
-        if (ok) return true;
-    }
-    return false;
-}
 
 __global__ void __launch_bounds__(WG2_THREADS)
 conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
@@ -1775,7 +1759,11 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     const size_t smem_wg2 = std::max(3 * (size_t)WG2_REC, 2 * (9 * line_f + dyl_f)) * 4;
     GNBV_REQUIRE(smem_wg2 <= 200 * 1024, "gnbv_encoder_backward: grid too large for the conv2 wgrad staging buffers");
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
-    if (conv2_tc_mode() & 8) {
+    int nrec_wg2 = w.nblk_wg2;
+    if (conv2_tc_mode() & 16) {
+        rc = launch_conv2_wgrad_staged(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, &nrec_wg2, stream);
+        if (rc) return rc;
+    } else if (conv2_tc_mode() & 8) {
         rc = launch_conv2_wgrad_mma(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, w.wg2_pps, stream);
         if (rc) return rc;
     } else {
@@ -1783,7 +1771,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
                                                                            d.G2, B * d.G2 * d.G2, w.wg2_pps);
     }
     GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
-    reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, w.nblk_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
+    reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, nrec_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);
     stage_mark(GNBV_ST_BWD_CONV2_DGRAD, stream);
     int nrec_dg;

@@ -376,6 +376,93 @@ def check_conv1_wgrad(G, B=1):
     print("G", G, "conv1 wgrad max err", werr, "db err", berr)
     assert werr < 1e-10 and berr < 1e-10
 
+
+def pad_mod32(n, r):
+    v = (n // 32) * 32 + r
+    return v if v >= n else v + 32
+
+
+def wgrad_staged(y1, sc, sh, dy2cl, G1, G2, B, nblocks):
+    """conv2_wgrad_staged_kernel: groups of 4 output rows staged as 27 y1 lines + 4 dy2 lines; slot t <-> (row t, z),
+    slot t+4 <-> (row t, z+1); n-tiles dealt round-robin to 8 warps."""
+    P1, P2 = G1 ** 3, G2 ** 3
+    LP, DP = pad_mod32(G1 * C, 4), pad_mod32(G2 * C, 8)
+    NYG = -(-G2 // 4)
+    total = B * G2 * NYG
+    gpb = -(-total // nblocks)
+    nblk = -(-total // gpb)
+    NTW = -(-2 * NT // 8)
+    rec = np.zeros((nblk, C * C * NT + C))
+    nzp = (G2 + 1) // 2
+    for blk in range(nblk):
+        acc = np.zeros((8, NTW, 32, 4))
+        db_lo, db_hi = np.zeros(32), np.zeros(32)
+        for grp in range(blk * gpb, min(total, blk * gpb + gpb)):
+            b, rem = divmod(grp, G2 * NYG)
+            x2, yg = divmod(rem, NYG)
+            y20 = yg * 4
+            nrows = min(4, G2 - y20)
+            xs = np.full(27 * LP + 4 * DP, np.nan)                       # unwritten smem must never be read
+            for i in range(3):
+                for yl in range(2 * nrows + 1):
+                    src = (b * P1 + ((2 * x2 + i) * G1 + (2 * y20 + yl)) * G1) * C
+                    xs[(i * 9 + yl) * LP:(i * 9 + yl) * LP + G1 * C] = y1[src:src + G1 * C]
+            for r in range(nrows):
+                src = (b * P2 + (x2 * G2 + y20 + r) * G2) * C
+                xs[27 * LP + r * DP:27 * LP + r * DP + G2 * C] = dy2cl[src:src + G2 * C]
+            for zp in range(nzp):
+                za, zb = 2 * zp, 2 * zp + 1
+                vb, zbc = zb < G2, min(zb, G2 - 1)
+                a = []
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    vrow, tc = t < nrows, min(t, nrows - 1)
+                    da = 27 * LP + tc * DP + za * C + g
+                    dbb = 27 * LP + tc * DP + zbc * C + g
+                    a0 = xs[da] if vrow else 0.0
+                    a1 = xs[da + 8] if vrow else 0.0
+                    a2 = xs[dbb] if (vrow and vb) else 0.0
+                    a3 = xs[dbb + 8] if (vrow and vb) else 0.0
+                    db_lo[lane] += a0 + a2; db_hi[lane] += a1 + a3
+                    a.append((a0, a1, a2, a3))
+                for warp in range(8):
+                    hf = warp & 1
+                    for k in range(NTW):
+                        nt = warp + 8 * k
+                        if nt >= 2 * NT: continue
+                        tap = nt >> 1
+                        i, r9 = divmod(tap, 9)
+                        jy, l = divmod(r9, 3)
+                        bfr = []
+                        for lane in range(32):
+                            g, t = lane >> 2, lane & 3
+                            tc = min(t, nrows - 1)
+                            line = (i * 9 + 2 * tc + jy) * LP + l * C + 8 * hf + g
+                            ci = 8 * hf + g
+                            x0 = max(sc[ci] * xs[line + 2 * za * C] + sh[ci], 0.0)
+                            x1 = max(sc[ci] * xs[line + 2 * zbc * C] + sh[ci], 0.0)
+                            assert not (np.isnan(x0) or np.isnan(x1))
+                            bfr.append((x0, x1))
+                        mma(acc[warp, k], a, bfr)
+        for warp in range(8):
+            hf = warp & 1
+            for k in range(NTW):
+                nt = warp + 8 * k
+                if nt >= 2 * NT: continue
+                tap = nt >> 1
+                for lane in range(32):
+                    g, t = lane >> 2, lane & 3
+                    for e in range(4):
+                        co, ci = g + 8 * (e >> 1), 8 * hf + 2 * t + (e & 1)
+                        rec[blk, (co * C + ci) * NT + tap] = acc[warp, k, lane, e]
+        for lane in range(32):
+            g, t = lane >> 2, lane & 3
+            if t == 0:
+                rec[blk, C * C * NT + g] = sum(db_lo[4 * g + tt] for tt in range(4))
+                rec[blk, C * C * NT + 8 + g] = sum(db_hi[4 * g + tt] for tt in range(4))
+    tot = rec.sum(0)
+    return tot[:C * C * NT], tot[C * C * NT:]
+
 def check(G1, B=1):
     G2 = (G1 - 3) // 2 + 1
     x = torch.randn(B, C, G1, G1, G1, dtype=torch.float64)           # pre-BN y1, NCDHW
@@ -405,6 +492,11 @@ def check(G1, B=1):
     werr = np.abs(dW - wt_ref.grad.numpy().reshape(-1)).max()
     berr = np.abs(db - b_ref.grad.numpy()).max()
     print("G1", G1, "wgrad max err", werr, "db err", berr)
+    assert werr < 1e-11 and berr < 1e-11
+    dW, db = wgrad_staged(y1_cl, sc.numpy(), sh.numpy(), dy2cl, G1, G2, B, nblocks=3)
+    werr = np.abs(dW - wt_ref.grad.numpy().reshape(-1)).max()
+    berr = np.abs(db - b_ref.grad.numpy()).max()
+    print("G1", G1, "staged wgrad max err", werr, "db err", berr)
     assert werr < 1e-11 and berr < 1e-11
 
 

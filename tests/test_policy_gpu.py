@@ -265,7 +265,8 @@ def test_encoder_forward_with_a_non_ternary_grid():
             assert rel_err(pol.features_extractor(obs.to(DEV)).cpu(), ref.features_extractor(obs)) < RTOL
 
 
-@pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0"}, {"GNBV_CONV2_TC": "2"}, {"GNBV_CONV2_TC": "6"},
+@pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0"}, {"GNBV_CONV2_TC": "2"}, {"GNBV_CONV2_TC": "6"}, {"GNBV_CONV2_TC": "14"},
+                                 {"GNBV_CONV2_TC": "30"},
                                  {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"}, {"GNBV_CONV1_MMA": "3"}],
                          ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
 def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
