@@ -269,6 +269,8 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* wsm = reinterpret_cast<float4*>(smem_raw);                           // [tap][q][lane]
     float* red = reinterpret_cast<float*>(smem_raw + (size_t)WSM_FLOAT4 * 16);   // [warps][32]
+    __shared__ int row_src[ROWS_PER_ITEM], row_dst[ROWS_PER_ITEM];
+    __shared__ uint32_t row_ok[ROWS_PER_ITEM];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
 
     // B[k = co][n = ci] = W2[co][ci][tap]; thread (g,t) of n-tile j reads co = 4t..4t+3 for ci = 8j + g
@@ -297,36 +299,32 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
             if (r < cl.chunks) break;
             r -= cl.chunks;
         }
-        const int row0 = r * ROWS_PER_ITEM + warp * ROWS_PER_WARP;
         const float inv_nz = 1.0f / (float)cl.nz, inv_ny = 1.0f / (float)cl.ny;
-        // per row: dy2 offset of the (di,dj,dl) = (0,0,0) source voxel, output voxel index, validity bits.
-        // The thread's rows are v0, v0 + 8, v0 + 16, ...: the first one is decoded by division, the others by stepping the
-        // (xi, yi, zi) counter 8 voxels forward with carries.
+        // per row: dy2 offset of the (di,dj,dl) = (0,0,0) source voxel, output voxel index, validity bits.  Decoding a row
+        // costs ~40 instructions; instead of every thread decoding its own 8 rows, the block decodes the item's 256 rows
+        // once (2 per thread) into shared memory and every thread picks its rows up from there.
+        for (int rr = tid; rr < ROWS_PER_ITEM; rr += MMA_THREADS) {
+            const int v = r * ROWS_PER_ITEM + rr;
+            const bool in = v < cl.nvox;
+            const int vv = in ? v : 0;
+            const int q = fast_div(vv, inv_nz), zi = vv - q * cl.nz, xi = fast_div(q, inv_ny), yi = q - xi * cl.ny;
+            row_src[rr] = ((xi * G2 + yi) * G2 + zi) * C;
+            row_dst[rr] = in ? ((2 * xi + cl.cx) * G1 + (2 * yi + cl.cy)) * G1 + (2 * zi + cl.cz) : -1;
+            // bit 2a: source index (coordinate - 0) < G2;  bit 2a+1: (coordinate - 1) >= 0
+            row_ok[rr] = in ? ((xi < G2 ? 1u : 0u) | (xi >= 1 ? 2u : 0u) | (yi < G2 ? 4u : 0u) | (yi >= 1 ? 8u : 0u) |
+                               (zi < G2 ? 16u : 0u) | (zi >= 1 ? 32u : 0u))
+                            : 0u;
+        }
+        __syncthreads();
         int src[MT][2], dst[MT][2];
         uint32_t okb[MT][2];
-        {
-            const int v0 = row0 + g;
-            const int q0 = fast_div(v0, inv_nz);
-            int zi = v0 - q0 * cl.nz, xi = fast_div(q0, inv_ny), yi = q0 - xi * cl.ny;
 #pragma unroll
-            for (int m = 0; m < MT; ++m)
+        for (int m = 0; m < MT; ++m)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const bool in = row0 + m * 16 + g + 8 * h < cl.nvox;
-                    src[m][h] = in ? ((xi * G2 + yi) * G2 + zi) * C : 0;
-                    dst[m][h] = in ? ((2 * xi + cl.cx) * G1 + (2 * yi + cl.cy)) * G1 + (2 * zi + cl.cz) : -1;
-                    // bit 2a: source index (coordinate - 0) < G2;  bit 2a+1: (coordinate - 1) >= 0
-                    uint32_t bits = 0;
-                    if (in) {
-                        bits = (xi < G2 ? 1u : 0u) | (xi >= 1 ? 2u : 0u) | (yi < G2 ? 4u : 0u) | (yi >= 1 ? 8u : 0u) |
-                               (zi < G2 ? 16u : 0u) | (zi >= 1 ? 32u : 0u);
-                    }
-                    okb[m][h] = bits;
-                    zi += 8;
-                    while (zi >= cl.nz) { zi -= cl.nz; ++yi; }
-                    while (yi >= cl.ny) { yi -= cl.ny; ++xi; }
-                }
-        }
+            for (int h = 0; h < 2; ++h) {
+                const int rr = warp * ROWS_PER_WARP + m * 16 + g + 8 * h;
+                src[m][h] = row_src[rr]; dst[m][h] = row_dst[rr]; okb[m][h] = row_ok[rr];
+            }
         float acc[MT][2][4];
 #pragma unroll
         for (int m = 0; m < MT; ++m)
@@ -558,8 +556,10 @@ conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ s
 // t+4 <-> (row t, z+1).  With that choice the four t-lanes of a fragment load read four DIFFERENT staged lines, and the
 // line pitch is padded to 4 (mod 32) floats (dy2 lines: 8 mod 32), so the 32 lanes of every LDS hit 32 different banks
 // -- positions of one line alone are always 32 floats apart and would collide four ways.
-// The 54 n-tiles (27 taps x 2 channel halves) are dealt round-robin to the 8 warps (<= 7 each = 28 accumulators).
-constexpr int WGS_THREADS = 256;
+// The 54 n-tiles (27 taps x 2 channel halves) are dealt round-robin to the 16 warps (<= 4 each = 16 accumulators); with one
+// block per SM (120 KB of stages) that is 4 warps per scheduler -- at 8 warps (2 per scheduler) the dependent
+// LDS -> BN/ReLU -> split -> HMMA chains were not covered (measured 0.50 ms, tensor pipe 30 % busy).
+constexpr int WGS_THREADS = 512;
 constexpr int WGS_WARPS = WGS_THREADS / 32;
 constexpr int WGS_NT = (2 * NTAPS + WGS_WARPS - 1) / WGS_WARPS;      // 7 n-tiles per warp
 constexpr int WGS_ROWS = 4;
@@ -581,7 +581,7 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
     const int NYG = (G2 + WGS_ROWS - 1) / WGS_ROWS;
     const uint32_t line_bytes = (uint32_t)G1 * C * 4, dy_bytes = (uint32_t)G2 * C * 4;
     // BN1 scale / shift of the two input channels this lane supplies as B columns: ci = 8*hf + g
-    // (n-tile nt = warp + 8k <-> tap nt >> 1, channel half nt & 1 = warp & 1: a warp only ever sees one channel half)
+    // (n-tile nt = warp + 16k <-> tap nt >> 1, channel half nt & 1 = warp & 1: a warp only ever sees one channel half)
     const int hf = warp & 1;
     const float scv = stat1[2 * C + 8 * hf + g], shv = stat1[3 * C + 8 * hf + g];
     float acc[WGS_NT][4];

@@ -384,18 +384,19 @@ def pad_mod32(n, r):
 
 def wgrad_staged(y1, sc, sh, dy2cl, G1, G2, B, nblocks):
     """conv2_wgrad_staged_kernel: groups of 4 output rows staged as 27 y1 lines + 4 dy2 lines; slot t <-> (row t, z),
-    slot t+4 <-> (row t, z+1); n-tiles dealt round-robin to 8 warps."""
+    slot t+4 <-> (row t, z+1); n-tiles dealt round-robin to 16 warps."""
     P1, P2 = G1 ** 3, G2 ** 3
     LP, DP = pad_mod32(G1 * C, 4), pad_mod32(G2 * C, 8)
     NYG = -(-G2 // 4)
     total = B * G2 * NYG
     gpb = -(-total // nblocks)
     nblk = -(-total // gpb)
-    NTW = -(-2 * NT // 8)
+    NW = 16
+    NTW = -(-2 * NT // NW)
     rec = np.zeros((nblk, C * C * NT + C))
     nzp = (G2 + 1) // 2
     for blk in range(nblk):
-        acc = np.zeros((8, NTW, 32, 4))
+        acc = np.zeros((NW, NTW, 32, 4))
         db_lo, db_hi = np.zeros(32), np.zeros(32)
         for grp in range(blk * gpb, min(total, blk * gpb + gpb)):
             b, rem = divmod(grp, G2 * NYG)
@@ -425,10 +426,10 @@ def wgrad_staged(y1, sc, sh, dy2cl, G1, G2, B, nblocks):
                     a3 = xs[dbb + 8] if (vrow and vb) else 0.0
                     db_lo[lane] += a0 + a2; db_hi[lane] += a1 + a3
                     a.append((a0, a1, a2, a3))
-                for warp in range(8):
+                for warp in range(NW):
                     hf = warp & 1
                     for k in range(NTW):
-                        nt = warp + 8 * k
+                        nt = warp + NW * k
                         if nt >= 2 * NT: continue
                         tap = nt >> 1
                         i, r9 = divmod(tap, 9)
@@ -444,10 +445,10 @@ def wgrad_staged(y1, sc, sh, dy2cl, G1, G2, B, nblocks):
                             assert not (np.isnan(x0) or np.isnan(x1))
                             bfr.append((x0, x1))
                         mma(acc[warp, k], a, bfr)
-        for warp in range(8):
+        for warp in range(NW):
             hf = warp & 1
             for k in range(NTW):
-                nt = warp + 8 * k
+                nt = warp + NW * k
                 if nt >= 2 * NT: continue
                 tap = nt >> 1
                 for lane in range(32):

@@ -267,7 +267,8 @@ def test_encoder_forward_with_a_non_ternary_grid():
 
 @pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0"}, {"GNBV_CONV2_TC": "2"}, {"GNBV_CONV2_TC": "6"}, {"GNBV_CONV2_TC": "14"},
                                  {"GNBV_CONV2_TC": "30"},
-                                 {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"}, {"GNBV_CONV1_MMA": "3"}],
+                                 {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"}, {"GNBV_CONV1_MMA": "3"},
+                                 {"GNBV_GEMM_MMA": "0"}, {"GNBV_GEMM_MMA": "1"}],
                          ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
 def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
     """Defaults: GNBV_CONV2_TC=14 (mma.sync conv2 forward + data gradient + weight gradient) and the GNBV_CONV1_MMA default
@@ -278,7 +279,7 @@ def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
     import subprocess, sys
     here = os.path.abspath(__file__)
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
-                          "encoder_forward_backward_vs_torch or policy_matches_reference_golden_g20 or non_ternary"],
+                          "encoder_forward_backward_vs_torch or policy_matches_reference_golden_g20 or non_ternary or sgemm_modes"],
                          env={**os.environ, **env}, capture_output=True, text=True, timeout=900,
                          cwd=os.path.dirname(os.path.dirname(here)))
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
