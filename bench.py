@@ -352,12 +352,17 @@ def run_native(args, rank, world):
                      "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_grid,
                      "voxelize_algorithmic_bytes_per_step": N * (b_vox + b_cov)},
-        "compute_kernels": {"note": "conv2 forward / dgrad / wgrad run on the tensor cores as mma.sync 3xTF32 implicit GEMMs "
-                                    "(GNBV_CONV2_TC=%s; plain tf32/bf16 operands would break the 1e-4 parity budget, the "
-                                    "hi/lo split keeps fp32-level error at 3 MMAs per product); conv1 and the Linear layers "
-                                    "are fp32 CUDA-core kernels.  tflops = ALGORITHMIC fp32 flops / time, against the nominal "
-                                    "fp32 FMA peak %.1f TFLOP/s (no measured denominator exists for it)"
-                                    % (os.environ.get("GNBV_CONV2_TC", "14 (default)"), fp32_peak),
+        "compute_kernels": {"note": "conv1 forward / weight gradient and conv2 forward / data gradient / weight gradient run on the "
+                                    "tensor cores as mma.sync (m16n8k8) implicit GEMMs with split-precision 3xTF32 operands "
+                                    "(plain tf32/bf16 operands would break the 1e-4 parity budget; the hi/lo split keeps "
+                                    "fp32-level error at 3 MMAs per product; the tri-class conv1 input is exact in TF32 and "
+                                    "is not split).  The Linear layers use the fp32 CUDA-core GEMM unless GNBV_GEMM_MMA=1.  "
+                                    "tflops = ALGORITHMIC fp32 flops / time against the nominal fp32 FMA peak %.1f TFLOP/s "
+                                    "(no measured denominator exists for it); the mma.sync TF32 path itself tops out near "
+                                    "238 TFLOP/s on B200 (HMMA.1688.F32.TF32 issue rate measured with ncu), i.e. 79 TFLOP/s "
+                                    "of fp32-equivalent work after the 3x split" % fp32_peak,
+                            "kernel_modes": {"GNBV_CONV2_TC": _lib.lib().gnbv_kernel_mode(0), "GNBV_CONV1_MMA": _lib.lib().gnbv_kernel_mode(1),
+                                             "GNBV_GEMM_MMA": _lib.lib().gnbv_kernel_mode(2)},
                             "kernels": compute},
         "e2e": {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / K},

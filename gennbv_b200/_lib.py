@@ -34,6 +34,7 @@ class EncoderGrads(ctypes.Structure):
 # name -> (restype, argtypes); mirrors include/gennbv_b200.h one to one
 SIGNATURES = {
     "gnbv_abi_version": (c_int, []),
+    "gnbv_kernel_mode": (c_int, [c_int]),
     "gnbv_last_error": (ctypes.c_char_p, []),
     "gnbv_profile_enable": (c_int, [c_int]),
     "gnbv_profile_elapsed_ms": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),

@@ -1,6 +1,8 @@
 // api.cu -- error reporting + ABI version of libgennbv_b200.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace gnbv {
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -10,6 +12,27 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 }  // namespace gnbv
+
+// ---- kernel-variant switches.  Every variant is parity-tested (tests/test_policy_gpu.py re-runs the encoder parity tests
+// under each setting); the defaults are the fastest measured on B200 at B = 256, 64^3 (profiles/).
+//   GNBV_CONV2_TC  (bit mask) 2 = mma.sync forward, 4 = mma.sync data gradient, 8 = mma.sync weight gradient (register
+//                  path), 16 = TMA-staged weight gradient (overrides 8), 32 = its hoisted-offset variant; 1 = tcgen05 forward
+//                  (conv2_tc.cu; slower, staging-bound); 0 = fp32 CUDA-core kernels.
+//   GNBV_CONV1_MMA (bit mask) 1 = conv1 forward on the tensor cores, 2 = conv1 weight gradient; 0 = CUDA-core TMA kernels.
+//   GNBV_GEMM_MMA  1 = mma.sync 3xTF32 GEMM for the Linear layers, 0 = fp32 CUDA-core GEMM.
+namespace gnbv {
+static int env_mode(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+int conv2_tc_mode() { static const int m = env_mode("GNBV_CONV2_TC", 30); return m; }
+int conv1_mma_mode() { static const int m = env_mode("GNBV_CONV1_MMA", 3); return m; }
+int gemm_mma_mode() { static const int m = env_mode("GNBV_GEMM_MMA", 0); return m; }
+}  // namespace gnbv
+
+extern "C" int gnbv_kernel_mode(int which) {
+    return which == 0 ? gnbv::conv2_tc_mode() : which == 1 ? gnbv::conv1_mma_mode() : which == 2 ? gnbv::gemm_mma_mode() : -1;
+}
 
 extern "C" int gnbv_abi_version(void) { return GNBV_ABI_VERSION; }
 extern "C" const char* gnbv_last_error(void) { return gnbv::g_err; }

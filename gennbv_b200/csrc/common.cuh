@@ -12,6 +12,11 @@ namespace gnbv {
 void set_error(const char* fmt, ...);
 void stage_mark(int id, cudaStream_t stream);      // no-op unless gnbv_profile_enable(1)
 
+// Kernel-variant switches (api.cu; environment variables read once per process, see gnbv_kernel_mode in the header).
+int conv2_tc_mode();      // GNBV_CONV2_TC
+int conv1_mma_mode();     // GNBV_CONV1_MMA
+int gemm_mma_mode();      // GNBV_GEMM_MMA
+
 #define GNBV_REQUIRE(cond, ...)                 \
     do {                                        \
         if (!(cond)) {                          \

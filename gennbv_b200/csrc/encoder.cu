@@ -34,23 +34,6 @@ constexpr int CONV2_ZT = 4;       // output voxels (along z) per thread
 
 constexpr int PART_STRIDE = 2 * C1 + 4;      // per block: mean[16], M2[16], count, pad
 
-// GNBV_CONV2_TC selects the conv2 kernels (bit mask, read once per process).  Default 14 = the three mma.sync 3xTF32
-// kernels of conv2_mma.cu (bit 2 forward, bit 4 data gradient, bit 8 weight gradient): measured on B200 at B = 256, 64^3:
-// forward 0.557 -> 0.283 ms, dgrad 0.838 -> 0.602 ms, wgrad 0.699 -> 0.581 ms against the CUDA-core kernels (profiles/r01p).
-// 0 = CUDA-core kernels; 1 = tcgen05 forward (conv2_tc.cu, slower: staging-bound).  All variants are parity-green.
-static int conv2_tc_mode() {
-    static const int mode = []() { const char* e = getenv("GNBV_CONV2_TC"); return e ? atoi(e) : 14; }();
-    return mode;
-}
-
-// GNBV_CONV1_MMA: bit 1 = conv1 forward on the tensor cores (conv1_fwd_mma_kernel), bit 2 = conv1 weight gradient
-// (conv1_wgrad_mma_kernel).  Default 3: measured on B200 at B = 256, 64^3 (profiles/r01r): forward 0.434 -> 0.250 ms, weight
-// gradient 0.486 -> 0.433 ms against the CUDA-core TMA kernels (0), which stay available and tested.
-static int conv1_mma_mode() {
-    static const int mode = []() { const char* e = getenv("GNBV_CONV1_MMA"); return e ? atoi(e) : 3; }();
-    return mode;
-}
-
 // Block-level (count, mean, M2) of `nv` values per thread and channel (acc[k][c], k < nv valid ones), written to
 // part[PART_STRIDE].  Two-pass inside each warp (mean first, then centred squares) and Chan's merge across warps:
 // no E[x^2] - mean^2 cancellation anywhere.
@@ -1761,7 +1744,8 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
     int nrec_wg2 = w.nblk_wg2;
     if (conv2_tc_mode() & 16) {
-        rc = launch_conv2_wgrad_staged(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, &nrec_wg2, stream);
+        rc = launch_conv2_wgrad_staged(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2,
+                                       (conv2_tc_mode() & 32) != 0, &nrec_wg2, stream);
         if (rc) return rc;
     } else if (conv2_tc_mode() & 8) {
         rc = launch_conv2_wgrad_mma(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, w.wg2_pps, stream);

@@ -272,12 +272,6 @@ sgemm_mma_kernel(GemmArgs g) {
             }
 }
 
-// GNBV_GEMM_MMA: 1 = tensor-core (mma.sync 3xTF32) GEMM for the encoder / policy contractions, 0 = fp32 CUDA-core GEMM.
-static int gemm_mma_mode() {
-    static const int mode = []() { const char* e = getenv("GNBV_GEMM_MMA"); return e ? atoi(e) : 0; }();
-    return mode;
-}
-
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C, int64_t ldc, int M, int N,
                                      int splits, const float* __restrict__ bias, int relu) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -30,6 +30,9 @@ extern "C" {
 #define GNBV_ABI_VERSION 1
 
 int gnbv_abi_version(void);
+/* Kernel variants in effect for this process: which = 0 -> GNBV_CONV2_TC, 1 -> GNBV_CONV1_MMA, 2 -> GNBV_GEMM_MMA
+ * (environment variables read once; defaults and bit meanings in gennbv_b200/csrc/api.cu). */
+int gnbv_kernel_mode(int which);
 const char* gnbv_last_error(void);
 
 /* ---- optional stage timing (measurement aid, not on the reference's API surface) ----

@@ -62,15 +62,18 @@ def test_sgemm_modes(M, N, K):
     Ad, Bd = A.to(DEV), Bm.to(DEV)
     At, Bt = A.t().contiguous().to(DEV), Bm.t().contiguous().to(DEV)
     scale = float(want.abs().max())
+    # fp32 FMA GEMM: 2e-6.  The tensor-core GEMM (GNBV_GEMM_MMA=1: 3xTF32 operands, ~2^-21 per product, and the tensor core's
+    # truncating fp32 accumulation over K) stays an order of magnitude inside the 1e-4 parity budget.
+    tol = 2e-5 if _lib.lib().gnbv_kernel_mode(2) & 1 else 2e-6
     for (a, sa), (b, sb) in [((Ad, (K, 1)), (Bd, (N, 1))), ((Ad, (K, 1)), (Bt, (1, K))), ((At, (1, M)), (Bd, (N, 1))),
                              ((At, (1, M)), (Bt, (1, K)))]:
         C = torch.full((M, N), float("nan"), device=DEV)
         ops.sgemm(a, sa, b, sb, C, M, N, K)
-        assert float((C.cpu().double() - want).abs().max()) / scale < 2e-6
+        assert float((C.cpu().double() - want).abs().max()) / scale < tol
     bias = torch.randn(N, generator=g)
     C = torch.empty(M, N, device=DEV)
     ops.sgemm(Ad, (K, 1), Bd, (N, 1), C, M, N, K, bias=bias.to(DEV), relu=True)
-    assert float((C.cpu().double() - torch.relu(want + bias.double())).abs().max()) / scale < 2e-6
+    assert float((C.cpu().double() - torch.relu(want + bias.double())).abs().max()) / scale < tol
 
 
 def test_policy_matches_reference_golden_g20():
@@ -266,16 +269,16 @@ def test_encoder_forward_with_a_non_ternary_grid():
 
 
 @pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0"}, {"GNBV_CONV2_TC": "2"}, {"GNBV_CONV2_TC": "6"}, {"GNBV_CONV2_TC": "14"},
-                                 {"GNBV_CONV2_TC": "30"},
-                                 {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"}, {"GNBV_CONV1_MMA": "3"},
-                                 {"GNBV_GEMM_MMA": "0"}, {"GNBV_GEMM_MMA": "1"}],
+                                 {"GNBV_CONV2_TC": "62"}, {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"},
+                                 {"GNBV_GEMM_MMA": "1"}],
                          ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
 def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
-    """Defaults: GNBV_CONV2_TC=14 (mma.sync conv2 forward + data gradient + weight gradient) and the GNBV_CONV1_MMA default
-    of encoder.cu, exercised by every other test in this file.  Here the encoder forward/backward parity tests against
-    torch autograd (all grid sizes, eval and training BN), the non-ternary-grid test and the golden policy test are re-run
-    in a subprocess with the other settings -- CUDA-core conv2 kernels (0), partial mixes (2, 6), conv1 on CUDA cores (0) /
-    forward on tensor cores (1) / forward + weight gradient (3) -- so that every kernel variant stays parity-green."""
+    """Defaults (csrc/api.cu): GNBV_CONV2_TC=30 (mma.sync conv2 forward + data gradient + TMA-staged weight gradient),
+    GNBV_CONV1_MMA=3, GNBV_GEMM_MMA=0 -- exercised by every other test in this file.  Here the GEMM test, the encoder
+    forward/backward parity tests against torch autograd (all grid sizes, eval and training BN), the non-ternary-grid test and
+    the golden policy test are re-run in a subprocess with the other settings -- CUDA-core conv2 kernels (0), partial mixes
+    (2, 6), the register-path weight gradient (14), the hoisted staged one (62), conv1 on CUDA cores (0) / forward only on
+    tensor cores (1), the tensor-core GEMM (1) -- so that every kernel variant stays parity-green."""
     import subprocess, sys
     here = os.path.abspath(__file__)
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
