@@ -27,7 +27,7 @@ static int env_mode(const char* name, int dflt) {
 }
 int conv2_tc_mode() { static const int m = env_mode("GNBV_CONV2_TC", 30); return m; }
 int conv1_mma_mode() { static const int m = env_mode("GNBV_CONV1_MMA", 3); return m; }
-int gemm_mma_mode() { static const int m = env_mode("GNBV_GEMM_MMA", 0); return m; }
+int gemm_mma_mode() { static const int m = env_mode("GNBV_GEMM_MMA", 1); return m; }
 }  // namespace gnbv
 
 extern "C" int gnbv_kernel_mode(int which) {

@@ -270,15 +270,15 @@ def test_encoder_forward_with_a_non_ternary_grid():
 
 @pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0"}, {"GNBV_CONV2_TC": "2"}, {"GNBV_CONV2_TC": "6"}, {"GNBV_CONV2_TC": "14"},
                                  {"GNBV_CONV2_TC": "62"}, {"GNBV_CONV1_MMA": "0"}, {"GNBV_CONV1_MMA": "1"},
-                                 {"GNBV_GEMM_MMA": "1"}],
+                                 {"GNBV_GEMM_MMA": "0"}],
                          ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
 def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
     """Defaults (csrc/api.cu): GNBV_CONV2_TC=30 (mma.sync conv2 forward + data gradient + TMA-staged weight gradient),
-    GNBV_CONV1_MMA=3, GNBV_GEMM_MMA=0 -- exercised by every other test in this file.  Here the GEMM test, the encoder
+    GNBV_CONV1_MMA=3, GNBV_GEMM_MMA=1 -- exercised by every other test in this file.  Here the GEMM test, the encoder
     forward/backward parity tests against torch autograd (all grid sizes, eval and training BN), the non-ternary-grid test and
     the golden policy test are re-run in a subprocess with the other settings -- CUDA-core conv2 kernels (0), partial mixes
     (2, 6), the register-path weight gradient (14), the hoisted staged one (62), conv1 on CUDA cores (0) / forward only on
-    tensor cores (1), the tensor-core GEMM (1) -- so that every kernel variant stays parity-green."""
+    tensor cores (1), the fp32 CUDA-core GEMM (0) -- so that every kernel variant stays parity-green."""
     import subprocess, sys
     here = os.path.abspath(__file__)
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
