@@ -569,7 +569,6 @@ __host__ __device__ inline int pad_mod32(int n, int r) {             // smallest
     return v >= n ? v : v + 32;
 }
 
-template <bool HOIST>
 __global__ void __launch_bounds__(WGS_THREADS, 1)
 conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
                           float* __restrict__ part, int G1, int G2, int total_groups, int groups_per_block) {
@@ -588,15 +587,6 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
     float acc[WGS_NT][4];
 #pragma unroll
     for (int k = 0; k < WGS_NT; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
-    // HOIST: the staged-line offset of each of the warp's n-tiles (tap decode, line index, channel) is computed once per
-    // kernel instead of once per k-step -- that address arithmetic was ~2/3 of the instructions of the first version.
-    int loff[WGS_NT];
-#pragma unroll
-    for (int k = 0; k < WGS_NT; ++k) {
-        const int tap = min((warp + WGS_WARPS * k) >> 1, NTAPS - 1);
-        const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
-        loff[k] = (i * 9 + jy) * LP + l * C + 8 * hf + g;
-    }
     float db_lo = 0.f, db_hi = 0.f;
     const int g0 = blockIdx.x * groups_per_block, g1 = min(total_groups, g0 + groups_per_block);
     if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init_fence(); }
@@ -638,7 +628,6 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
         const float* dys = xs + 27 * LP;
         const bool vrow = t < nrows;
         const int tc = min(t, nrows - 1);                   // rows past the grid alias the last valid row (their A is 0)
-        const float* xrow = xs + 2 * tc * LP;
         for (int zp = 0; zp < nzp; ++zp) {
             const int za = 2 * zp, zb = za + 1;
             const bool vb = zb < G2;
@@ -656,14 +645,10 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
                 const int nt = warp + WGS_WARPS * k;
                 if (nt < 2 * NTAPS) {                       // warp-uniform
                     // B (k = position, n = ci): b0 = x[row t, 2*za + l][ci], b1 = x[row t, 2*zb + l][ci]
-                    const float* line;
-                    if (HOIST) {
-                        line = xrow + loff[k];
-                    } else {
-                        const int tap = nt >> 1;
-                        const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
-                        line = xs + (i * 9 + 2 * tc + jy) * LP + l * C + 8 * hf + g;
-                    }
+                    // (precomputing the per-n-tile line offsets once per kernel was measured no faster: 3.41 vs 3.33 ms/step)
+                    const int tap = nt >> 1;
+                    const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
+                    const float* line = xs + (i * 9 + 2 * tc + jy) * LP + l * C + 8 * hf + g;
                     const float x0 = fmaxf(fmaf(scv, line[2 * za * C], shv), 0.f);
                     const float x1 = fmaxf(fmaf(scv, line[2 * zbc * C], shv), 0.f);
                     uint32_t bh0, bl0, bh1, bl1;
@@ -744,21 +729,19 @@ int launch_conv2_wgrad_mma(const float* y1, const float* stat1, const float* dy2
 }
 
 int launch_conv2_wgrad_staged(const float* y1, const float* stat1, const float* dy2cl, float* part, int B, int G1, int G2,
-                              int max_blocks, int hoist, int* nblocks_out, cudaStream_t stream) {
+                              int max_blocks, int* nblocks_out, cudaStream_t stream) {
     const int LP = pad_mod32(G1 * C, 4), DP = pad_mod32(G2 * C, 8);
     const size_t smem = (size_t)2 * (27 * LP + WGS_ROWS * DP) * 4;
     GNBV_REQUIRE(smem <= 200 * 1024, "conv2 wgrad: grid too large for the staged kernel's shared-memory lines");
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     const int total = B * G2 * (int)ceil_div(G2, WGS_ROWS);
     const int want = std::min(std::min(max_blocks, 148), total);
     const int gpb = (int)ceil_div(total, want), nblk = (int)ceil_div(total, gpb);
-    if (hoist) conv2_wgrad_staged_kernel<true><<<nblk, WGS_THREADS, smem, stream>>>(y1, stat1, dy2cl, part, G1, G2, total, gpb);
-    else conv2_wgrad_staged_kernel<false><<<nblk, WGS_THREADS, smem, stream>>>(y1, stat1, dy2cl, part, G1, G2, total, gpb);
+    conv2_wgrad_staged_kernel<<<nblk, WGS_THREADS, smem, stream>>>(y1, stat1, dy2cl, part, G1, G2, total, gpb);
     GNBV_LAUNCH_CHECK("conv2_wgrad_staged_kernel");
     *nblocks_out = nblk;
     return GNBV_OK;

@@ -25,8 +25,8 @@ int launch_conv2_wgrad_mma(const float* y1, const float* stat1, const float* dy2
                            int nblocks, int rows_per_block, cudaStream_t stream);
 
 // Same contract, TMA-staged (groups of four output rows in shared memory, bank-conflict-free fragment loads): launches at
-// most min(max_blocks, 148) blocks and reports how many records it wrote.  hoist != 0: per-n-tile line offsets precomputed.
+// most min(max_blocks, 148) blocks and reports how many records it wrote.
 int launch_conv2_wgrad_staged(const float* y1, const float* stat1, const float* dy2cl, float* part, int B, int G1, int G2,
-                              int max_blocks, int hoist, int* nblocks_out, cudaStream_t stream);
+                              int max_blocks, int* nblocks_out, cudaStream_t stream);
 
 }  // namespace gnbv

@@ -1744,8 +1744,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
     int nrec_wg2 = w.nblk_wg2;
     if (conv2_tc_mode() & 16) {
-        rc = launch_conv2_wgrad_staged(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2,
-                                       (conv2_tc_mode() & 32) != 0, &nrec_wg2, stream);
+        rc = launch_conv2_wgrad_staged(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, &nrec_wg2, stream);
         if (rc) return rc;
     } else if (conv2_tc_mode() & 8) {
         rc = launch_conv2_wgrad_mma(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, w.wg2_pps, stream);
