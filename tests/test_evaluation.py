@@ -89,3 +89,64 @@ def test_evaluation_loop_matches_reference_bookkeeping():
     np.testing.assert_allclose(torch.stack(er).numpy(), torch.stack(ep_rewards).numpy(), rtol=1e-6)
     np.testing.assert_allclose(mean_auc.cpu().numpy(), want_auc.numpy(), rtol=1e-6)
     assert sorted(accs) == sorted(want_acc.values()) and all(np.isfinite(a) and a > 0 for a in accs)
+
+
+class _FakeEvalEnv:
+    """Pure-torch stand-in for the wrapped eval env (50 envs x 30 steps, the constants the reference hard-codes): scripted
+    rewards, a time-out at step 30 for every env plus a few scripted early terminations, accuracies filled in on done."""
+    num_envs, max_episode_length, device = 50, 30, torch.device("cpu")
+
+    def __init__(self, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.rew = torch.rand(40, 50, generator=g)
+        self.early = {5: [3, 17], 12: [8], 29: [44]}           # step -> envs that terminate early (collisions)
+        self.t = 0
+        self.len = torch.zeros(50, dtype=torch.long)
+        self.acc = {}
+
+    def env_is_wrapped(self, cls):
+        return [False]
+
+    def reset(self):
+        self.t, self.acc = 0, {}
+        self.len.zero_()
+        return torch.zeros(50, 4), torch.zeros(50), torch.ones(50, dtype=torch.bool), {}, {}
+
+    def step(self, actions):
+        self.len += 1
+        dones = self.len >= self.max_episode_length
+        for e in self.early.get(self.t, []):
+            dones[e] = True
+        for e in dones.nonzero().flatten().tolist():
+            self.acc.setdefault(str(e), 0.25 + 0.01 * e + 0.001 * self.t)
+        self.len[dones] = 0
+        r = self.rew[self.t].clone()
+        self.t += 1
+        return torch.zeros(50, 4), r, dones, {}, self.acc
+
+    def render(self):
+        pass
+
+
+class _FakeModel:
+    def predict(self, obs, state=None, episode_start=None, deterministic=True):
+        return torch.zeros(50, 6, dtype=torch.long), state
+
+
+@pytest.mark.reference
+def test_evaluation_loop_equals_the_reference_function_on_a_scripted_env():
+    """The reference's own evaluate_policy_grid_obs (stable_baselines3/common/evaluation.py:136-347) and ours, driven by the
+    same scripted env and model on CPU tensors: episode rewards / lengths / accuracies in the same order, same mean AUC."""
+    import warnings
+    import ref_loader
+    ref_loader.load_reference()
+    from stable_baselines3.common.evaluation import evaluate_policy_grid_obs as ref_eval
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r_ref, l_ref, auc_ref, acc_ref = ref_eval(_FakeModel(), _FakeEvalEnv(7), n_eval_episodes=50, warn=False)
+    r, l, auc, acc = evaluate_policy_grid_obs(_FakeModel(), _FakeEvalEnv(7), n_eval_episodes=50)
+    assert len(r) == len(r_ref) == 50
+    np.testing.assert_allclose([float(x) for x in r], [float(x) for x in r_ref], rtol=1e-6)
+    assert [int(x) for x in l] == [int(x) for x in l_ref]
+    assert acc == acc_ref
+    np.testing.assert_allclose(auc.numpy(), auc_ref.numpy(), rtol=1e-6)
