@@ -32,6 +32,11 @@ WORKLOAD = ("BASELINE configs[1]: 256 envs/GPU x 128x128 synthetic depth x 64^3 
             "reward + termination/reset) + Hybrid_Encoder (3D-CNN) forward/backward on the 256 observations")
 
 
+CONFIG = {"workload": WORKLOAD, "envs_per_gpu": ENVS_PER_GPU, "depth": [H, W], "grid": G, "frames_rotated": FRAMES,
+          "l2": "per-step working set (prob+scanned+gt grids 0.8 GB, observations 0.28 GB, conv1 activations 0.49 GB) exceeds "
+                "the 126 MB L2; no explicit flush"}          # identical in both arms (the driver compares it)
+
+
 def algorithmic_bytes_per_env_step(P, V):
     """voxelize P*(4+4) + 64 + V*(4r+4w prob) + V*4 tri; coverage V*(4 gt + 4r + 4w scanned) + 4."""
     return P * 8 + 64 + V * 12, V * 12 + 4
@@ -166,8 +171,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3 * ENVS_PER_GPU / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "host CPU arm; ms_per_step extrapolated to 256 envs",
-                   "stages_ms_per_sample_step": {k: v * 1e3 for k, v in stages.items()}},
+        "config": CONFIG, "note": "host CPU arm; ms_per_step extrapolated to 256 envs",
+        "stages_ms_per_sample_step": {k: v * 1e3 for k, v in stages.items()},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -198,6 +203,69 @@ def build_native(wl, dev, host_frames):
     return env, sensor, policy
 
 
+def ppo_iteration(wl, dev, world, n_steps, batch_size=128, n_epochs=5, target_kl=0.05, iters=1):
+    """BASELINE configs[2] / [3]: one full PPO iteration through the public API -- `PPO_Grid_Obs.collect_rollouts()` (256 envs x
+    n_steps env.step + policy) and `train()` (n_epochs x minibatches of `batch_size`, gradient all-reduce when world > 1) --
+    after one untimed warm-up iteration.  Device time is bracketed by synchronisations; env-steps/s = envs * n_steps / total."""
+    import torch.distributed as dist
+    from gennbv_b200.config import Config_GenNBV_Train
+    from gennbv_b200.env import Env_Train_GenNBV
+    from gennbv_b200.ppo import PPO_Grid_Obs
+    from gennbv_b200.sensors import FrameListSensor
+    from gennbv_b200.wrapper import EnvWrapperGenNBVTrain
+
+    class Cfg(Config_GenNBV_Train):
+        class rewards(Config_GenNBV_Train.rewards):
+            only_positive_rewards = False
+
+    N = ENVS_PER_GPU
+    env = EnvWrapperGenNBVTrain(Env_Train_GenNBV(Cfg(), sim_device=str(dev), sensor=FrameListSensor(wl["frames"], dev),
+                                                 grid_gt=wl["scenes"].grid_gt, num_envs=N))
+    kw = dict(net_arch=[], features_extractor_kwargs=dict(
+        encoder_param={"hidden_shapes": [256, 256], "visual_dim": 256},
+        net_param={"transformer_params": [[1, 256], [1, 256]], "append_hidden_shapes": [256, 256]},
+        state_input_shape=(STATE_DIM,), visual_input_shape=(100, H, W)))
+    algo = PPO_Grid_Obs(env=env, learning_rate=1e-4, n_steps=n_steps, batch_size=batch_size, n_epochs=n_epochs, gamma=0.99,
+                        gae_lambda=0.95, clip_range=0.2, clip_range_vf=0.2, ent_coef=0.01, vf_coef=0.8, max_grad_norm=1,
+                        target_kl=target_kl, policy_kwargs=kw, seed=1, device=dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    algo._setup_learn()
+    algo.collect_rollouts()                 # warm-up iteration: allocations, graph capture, first touch of the 35 GB buffer
+    algo.train()
+    roll, train, opt_steps, stopped = [], [], [], []
+    for _ in range(iters):
+        sync(); t0 = time.perf_counter()
+        algo.collect_rollouts()
+        sync(); t1 = time.perf_counter()
+        before = algo._adam_step
+        algo.train()
+        sync(); t2 = time.perf_counter()
+        roll.append(t1 - t0); train.append(t2 - t1)
+        opt_steps.append(algo._adam_step - before); stopped.append(algo._last_train["stopped_epoch"])
+    mb_run = [algo._last_train["minibatches_logged"]]
+    t = torch.tensor([float(np.median(roll)), float(np.median(train))], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rollout_s, train_s = t.tolist()
+    n_mb = n_epochs * (-(-N * n_steps // batch_size))
+    out = {"workload": f"BASELINE configs[{2 if world == 1 else 3}]: {N} envs/GPU x {n_steps} steps rollout + {n_epochs} epochs x "
+                       f"minibatches of {batch_size} through PPO_Grid_Obs.collect_rollouts()/train(), target_kl={target_kl}",
+           "rollout_s": rollout_s, "train_s": train_s, "optimizer_steps": opt_steps[-1], "minibatches_scheduled": n_mb,
+           "minibatches_logged": mb_run[-1], "kl_stopped_epoch": stopped[-1],
+           "ms_per_minibatch_update": train_s * 1e3 / max(1, n_mb if stopped[-1] is None else (stopped[-1] + 1) * (n_mb // n_epochs)),
+           "env_steps_per_sec": world * N * n_steps / (rollout_s + train_s),
+           "rollout_env_steps_per_sec": world * N * n_steps / rollout_s, "cuda_graph": bool(algo._graphs),
+           "rollout_buffer_gb": algo.rollout_buffer.observations.numel() * 4 / 1e9}
+    del algo, env
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_native(args, rank, world):
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -207,6 +275,7 @@ def run_native(args, rank, world):
         import datetime
         # bounded collectives: a wedged peer makes the run fail after 3 minutes instead of hanging the box
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    from gennbv_b200 import dist as gdist
     N, V, P = ENVS_PER_GPU, G ** 3, H * W
     wl = make_workload(N, dev, seed=rank)
     K, Wm = args.steps, args.warmup
@@ -221,6 +290,7 @@ def run_native(args, rank, world):
         enc = policy.features_extractor
         grads = policy.encoder_grad_views()
         dfeat = torch.full((N, 256), 1.0 / N, device=dev)
+        overlap = gdist.OverlappedGradAllreduce(policy.grad_bucket, 4 + policy.linear_slice_offset)
         env.reset()
 
         def step(i, ev=None):
@@ -233,9 +303,14 @@ def run_native(args, rank, world):
             feats = enc._run_forward(obs, need_bwd=True, training=True)
             if ev is not None:
                 ev[5].record()
-            enc._run_backward(obs, feats, dfeat, N, True, enc._ws, grads=grads)
-            if world > 1:
-                dist.all_reduce(policy.flat_grads)         # PPO gradient all-reduce over NCCL/NVLink (configs[3])
+            # the next action exists once the forward is done: the host sensor frame of step i+1 can cross PCIe under the backward
+            sensor.prefetch_next()
+            # PPO gradient all-reduce over NCCL/NVLink (configs[3]): the Linear-layer slice (99.9 % of the bytes) is final
+            # after the first phase of the backward and travels under the convolution backward
+            enc._run_backward(obs, feats, dfeat, N, True, enc._ws, grads=grads, phases=1)
+            overlap.start_linear()
+            enc._run_backward(obs, feats, dfeat, N, True, enc._ws, grads=grads, phases=2)
+            overlap.finish()
             if ev is not None:
                 ev[6].record()
             return rew, feats
@@ -268,7 +343,7 @@ def run_native(args, rank, world):
     kernel_ms = {k: _lib.stage_ms(k) for k in _lib.ENCODER_STAGES}          # device time of each encoder stage, last timed step
     _lib.lib().gnbv_profile_enable(0)
     env._gym_env.profile_events = None
-    stage = lambda a, b: float(np.mean([e[a].elapsed_time(e[b]) for e in ev]))
+    stage = lambda a, b: float(np.median([e[a].elapsed_time(e[b]) for e in ev]))
     per_step = np.array([e[0].elapsed_time(e[6]) for e in ev])
     step_spread = {"min": float(per_step.min()), "median": float(np.median(per_step)), "max": float(per_step.max())}
     stages = {"env.step total": stage(0, 4), "scan_raycast": stage(1, 2), "grid_update+coverage": stage(2, 3),
@@ -312,79 +387,96 @@ def run_native(args, rank, world):
     ms_e2e = e0.elapsed_time(e1)
     h2d, d2h = sensor.bytes_per_frame, N * 4 + 4
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    del step, env, sensor, policy
+    torch.cuda.empty_cache()
 
     keys = list(stages)
-    t = torch.tensor([ms_total, ms_e2e] + [stages[k] for k in keys], device=dev, dtype=torch.float64)
+    kkeys = list(kernel_ms)
+    t = torch.tensor([ms_total, ms_e2e] + [stages[k] for k in keys] + [kernel_ms[k] for k in kkeys], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     vals = t.tolist()
     ms_total, ms_e2e = vals[0], vals[1]
-    stages = dict(zip(keys, vals[2:]))
+    stages = dict(zip(keys, vals[2:2 + len(keys)]))
+    kernel_ms = dict(zip(kkeys, vals[2 + len(keys):]))
+
+    # ---- BASELINE configs[2] (1 GPU) / configs[3] (N GPUs): a full PPO iteration through PPO_Grid_Obs
+    ppo = None
+    if not args.no_ppo:
+        ppo = ppo_iteration(wl, dev, world, n_steps=args.ppo_steps)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
-    b_vox, b_cov = algorithmic_bytes_per_env_step(P, V)
-    ms_grid = stages["grid_update+coverage"]
-    alg_grid = N * (V * 24 + 4)       # grid_update_kernel: prob r+w, scanned r+w, gt r, tri w = 24 B/voxel (+4 B coverage) per env
-    achieved = alg_grid / (ms_grid * 1e-3) / 1e9
-    G1 = (G - 3) // 2 + 1
-    G2 = (G1 - 3) // 2 + 1
-    flops = {"fwd.conv1": 2 * N * G1 ** 3 * 16 * 27, "bwd.conv1_wgrad": 2 * N * G1 ** 3 * 16 * 27,
-             "fwd.conv2": 2 * N * G2 ** 3 * 16 * 432, "bwd.conv2_wgrad": 2 * N * G2 ** 3 * 16 * 432,
-             "bwd.conv2_dgrad": 2 * N * G2 ** 3 * 16 * 432, "fwd.grid_fc": 2 * N * 16 * G2 ** 3 * 256,
-             "bwd.grid_fc": 4 * N * 16 * G2 ** 3 * 256}
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12            # nominal fp32 FMA peak (no measured denominator exists for it)
-    compute = {k: {"ms": kernel_ms[k], "gflop": v / 1e9, "tflops": v / (kernel_ms[k] * 1e-3) / 1e12,
-                   "frac_of_nominal_fp32_peak": v / (kernel_ms[k] * 1e-3) / 1e12 / fp32_peak} for k, v in flops.items()}
-    out = {
-        "metric": METRIC, "value": world * N * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": N, "depth": [H, W], "grid": G, "frames_rotated": FRAMES,
-                   "l2": "per-step working set (prob+scanned+gt grids 0.8 GB, observations 0.28 GB, conv1 activations 0.49 GB) "
-                         "exceeds the 126 MB L2; no explicit flush",
-                   "stages_ms": stages, "step_ms_spread": step_spread, "encoder_kernel_ms_last_step": kernel_ms},
-        "roofline": {"bound": "hbm", "kernel": "grid_update_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": 1569.4e6,
-                     "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_grid,
-                     "voxelize_algorithmic_bytes_per_step": N * (b_vox + b_cov)},
-        "compute_kernels": {"note": "conv1 forward / weight gradient and conv2 forward / data gradient / weight gradient run on the "
-                                    "tensor cores as mma.sync (m16n8k8) implicit GEMMs with split-precision 3xTF32 operands "
-                                    "(plain tf32/bf16 operands would break the 1e-4 parity budget; the hi/lo split keeps "
-                                    "fp32-level error at 3 MMAs per product; the tri-class conv1 input is exact in TF32 and "
-                                    "is not split).  The Linear layers use the same 3xTF32 mma.sync inner product (GNBV_GEMM_MMA=0: fp32 CUDA-core GEMM).  "
-                                    "tflops = ALGORITHMIC fp32 flops / time against the nominal fp32 FMA peak %.1f TFLOP/s "
-                                    "(no measured denominator exists for it); the mma.sync TF32 path itself tops out near "
-                                    "238 TFLOP/s on B200 (HMMA.1688.F32.TF32 issue rate measured with ncu), i.e. 79 TFLOP/s "
-                                    "of fp32-equivalent work after the 3x split" % fp32_peak,
-                            "kernel_modes": {"GNBV_CONV2_TC": _lib.lib().gnbv_kernel_mode(0), "GNBV_CONV1_MMA": _lib.lib().gnbv_kernel_mode(1),
-                                             "GNBV_GEMM_MMA": _lib.lib().gnbv_kernel_mode(2)},
-                            "kernels": compute},
-        "e2e": {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / K},
-        "gpu_launches": (launches or 0) * K, "gpu_launches_per_step": launches,
-        "clocks": clocks,
-    }
-    # the kernel that takes the most time in the step is a tensor-core one: report it against the MEASURED dense bf16 peak
-    # (sustained figure: the kernel is timed inside a long step).  Its arithmetic is fp32-equivalent through 3 TF32 MMAs per
-    # product at half the bf16 rate, on the warp-level mma.sync path, so a small fraction is expected -- stated, not hidden.
-    dom = max(("fwd.conv2", "bwd.conv2_wgrad", "bwd.conv2_dgrad", "bwd.grid_fc"), key=lambda k: kernel_ms[k])
     bf16_peak, bf16_src = 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         mp = json.load(open(pk))
         if mp.get("bf16_tflops_sustained"):
             bf16_peak, bf16_src = float(mp["bf16_tflops_sustained"]), "measured sustained cuBLAS bf16 (MEASURED_PEAKS.json)"
-    out["roofline_dominant"] = {
-        "bound": "tensor", "kernel": dom, "ms": kernel_ms[dom], "achieved": compute[dom]["tflops"], "peak": bf16_peak,
-        "unit": "TFLOP/s", "frac": compute[dom]["tflops"] / bf16_peak, "traffic": None, "peak_source": bf16_src,
-        "note": "achieved = algorithmic fp32 flops / live kernel time; the kernel issues 3x that on the tensor pipe (3xTF32), "
-                "TF32 runs at half the bf16 rate and mma.sync at about a fifth of the tcgen05 rate (measured: 238 TFLOP/s TF32), "
-                "so 79 TFLOP/s algorithmic is this path's ceiling; tensor-pipe busy fractions are in profiles/*ncu_full*"}
+    b_vox, b_cov = algorithmic_bytes_per_env_step(P, V)
+    G1 = (G - 3) // 2 + 1
+    G2 = (G1 - 3) // 2 + 1
+    D = STATE_DIM + V + 8192
+    y1_b, y2_b, w_fc = N * G1 ** 3 * 16 * 4, N * G2 ** 3 * 16 * 4, 256 * 16 * G2 ** 3 * 4
+    # per-kernel algorithmic work (SURVEY.md 8d style: the tensors a kernel must read and write once, reference dtypes) and
+    # fp32 flops; the binding roofline of a kernel is the larger of bytes / HBM peak and 3 x flops / (bf16 peak / 2) -- the
+    # contractions run as 3 TF32 MMAs per product (fp32-level accuracy, 1e-4 parity budget) and TF32 runs at half the bf16 rate
+    work = {
+        "scan_raycast": (N * P * 8 + N * 64, 0), "grid_update+coverage": (N * (V * 24 + 4), 0),
+        "fwd.conv1": (N * V * 4 + y1_b, 2 * N * G1 ** 3 * 16 * 27), "fwd.conv2": (y1_b + y2_b, 2 * N * G2 ** 3 * 16 * 432),
+        "fwd.grid_fc": (y2_b + w_fc, 2 * N * 16 * G2 ** 3 * 256), "bwd.grid_fc": (2 * y2_b + 2 * w_fc, 4 * N * 16 * G2 ** 3 * 256),
+        "bwd.conv2_wgrad": (y1_b + y2_b, 2 * N * G2 ** 3 * 16 * 432), "bwd.conv2_dgrad": (2 * y1_b + y2_b, 2 * N * G2 ** 3 * 16 * 432),
+        "bwd.conv1_wgrad": (2 * y1_b + N * V * 4, 2 * N * G1 ** 3 * 16 * 27)}
+    live = {"scan_raycast": stages["scan_raycast"], "grid_update+coverage": stages["grid_update+coverage"], **kernel_ms}
+    kernels = {}
+    for k, (nbytes, flops) in work.items():
+        ms = live[k]
+        t_hbm, t_tc = nbytes / (peak * 1e9) * 1e3, 3 * flops / (bf16_peak / 2 * 1e12) * 1e3
+        kernels[k] = {"ms": ms, "share_of_step": ms / (ms_total / K), "algorithmic_mb": nbytes / 1e6, "gflop_fp32": flops / 1e9,
+                      "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac_hbm": nbytes / (ms * 1e-3) / 1e9 / peak,
+                      "achieved_tflops_fp32_equiv": flops / (ms * 1e-3) / 1e12 if flops else None,
+                      "frac_tensor_3xtf32": (t_tc / ms) if flops else None, "bound": "hbm" if t_hbm >= t_tc else "tensor",
+                      "frac_of_binding_roofline": max(t_hbm, t_tc) / ms}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    dk = kernels[dom]
+    traffic = {"grid_update+coverage": 1569.4e6}.get(dom)        # ncu dram__bytes per launch where a capture of this kernel exists
+    if dk["bound"] == "hbm":
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac_hbm"],
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": work[dom][0]}
+    else:
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": dk["achieved_tflops_fp32_equiv"], "peak": bf16_peak, "unit": "TFLOP/s",
+                    "frac": dk["achieved_tflops_fp32_equiv"] / bf16_peak, "traffic": traffic, "peak_source": bf16_src,
+                    "algorithmic_flops_per_launch": work[dom][1]}
+    roofline["ms"] = dk["ms"]
+    roofline["share_of_step"] = dk["share_of_step"]
+    roofline["note"] = ("dominant kernel of the step by live device time (CUDA events on the launching stream inside the timed region); "
+                        "algorithmic bytes/flops per launch in DESIGN.md section 4; frac_of_binding_roofline in `kernels` "
+                        "compares with the larger of the HBM and 3xTF32 tensor floors")
+    gk = kernels["grid_update+coverage"]
+    out = {
+        "metric": METRIC, "value": world * N * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": CONFIG,
+        "stages_ms": stages, "step_ms_spread": step_spread, "encoder_kernel_ms": kernel_ms,
+        "roofline": roofline,
+        "roofline_hbm": {"bound": "hbm", "kernel": "grid_update_kernel", "achieved": gk["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                         "frac": gk["frac_hbm"], "traffic": 1569.4e6, "ms": gk["ms"],
+                         "traffic_source": "profiles/r01b_ncu_full_voxelize.txt (dram__bytes_read+write per launch)",
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": work["grid_update+coverage"][0],
+                         "voxelize_algorithmic_bytes_per_step": N * (b_vox + b_cov)},
+        "kernels": kernels,
+        "kernel_modes": {"GNBV_CONV2_TC": _lib.lib().gnbv_kernel_mode(0), "GNBV_CONV1_MMA": _lib.lib().gnbv_kernel_mode(1),
+                         "GNBV_GEMM_MMA": _lib.lib().gnbv_kernel_mode(2)},
+        "e2e": {"value": world * N * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / K, "prefetch": "host frame i+1 copied on a side stream under step i's backward"},
+        "gpu_launches": (launches or 0) * K, "gpu_launches_per_step": launches,
+        "clocks": clocks,
+    }
+    if ppo is not None:
+        out["ppo_iteration"] = ppo
     if world == 1 and not args.no_cpu_baseline:
         n, threads = 16, os.cpu_count() or 1
         wl_cpu = {"scenes": wl["scenes"], "frames": [{k: v[:n].cpu() for k, v in f.items()} for f in wl["frames"]]}
@@ -409,6 +501,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-envs", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the full PPO iteration record (BASELINE configs[2]/[3])")
+    ap.add_argument("--ppo-steps", type=int, default=128, help="n_steps of the PPO iteration record (reference default 128)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgennbv_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 
@@ -29,6 +29,22 @@ class EncoderGrads(ctypes.Structure):
     FIELDS = ["conv1_w", "conv1_b", "bn1_w", "bn1_b", "conv2_w", "conv2_b", "bn2_w", "bn2_b",
               "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b"]
     _fields_ = [(f, ctypes.c_void_p) for f in FIELDS]
+
+
+class PpoMinibatch(ctypes.Structure):
+    """gnbv_ppo_minibatch (include/gennbv_b200.h), field for field."""
+    _fields_ = [("enc", ctypes.POINTER(EncoderParams)), ("enc_grads", ctypes.POINTER(EncoderGrads)),
+                ("head_w", c_void_p), ("head_b", c_void_p), ("head_w_grad", c_void_p), ("head_b_grad", c_void_p),
+                ("nvec", ctypes.POINTER(c_int)), ("num_sub", c_int), ("feat_dim", c_int),
+                ("observations", c_void_p), ("obs_row_stride", c_int64),
+                ("actions", c_void_p), ("values", c_void_p), ("log_probs", c_void_p), ("advantages", c_void_p),
+                ("returns", c_void_p), ("storage_rows", c_void_p), ("rows_base", c_int64),
+                ("batch", c_int), ("grid_size", c_int), ("state_dim", c_int), ("normalize_advantage", c_int),
+                ("clip_range", c_double), ("clip_range_vf", c_double), ("ent_coef", c_double), ("vf_coef", c_double),
+                ("pg_coef", c_double), ("target_kl", c_double),
+                ("ctl", c_void_p), ("vote", c_void_p), ("log", c_void_p), ("log_capacity", c_int64),
+                ("enc_workspace", c_void_p), ("enc_workspace_bytes", c_size_t),
+                ("mb_workspace", c_void_p), ("mb_workspace_bytes", c_size_t)]
 
 
 # name -> (restype, argtypes); mirrors include/gennbv_b200.h one to one
@@ -59,6 +75,14 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnbv_encoder_backward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_void_p]),
+    "gnbv_encoder_backward_phase": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
+                                            c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_int, c_void_p]),
+    "gnbv_ppo_minibatch_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "gnbv_ppo_apply_workspace_bytes": (c_size_t, []),
+    "gnbv_ppo_minibatch_grads": (c_int, [ctypes.POINTER(PpoMinibatch), c_int, c_void_p]),
+    "gnbv_ppo_minibatch_scalars": (c_int, [ctypes.POINTER(PpoMinibatch), ctypes.POINTER(c_void_p)]),
+    "gnbv_ppo_minibatch_apply": (c_int, [ctypes.POINTER(PpoMinibatch), c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                         c_double, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p]),
     "gnbv_policy_heads_forward": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "gnbv_multicategorical_evaluate": (c_int, [c_void_p, c_int64, ctypes.POINTER(c_int), c_int, c_void_p, c_void_p,
                                                c_void_p, c_int, c_void_p]),

@@ -51,15 +51,20 @@ class TensorRolloutBuffer_Grid_Obs:
         self.values = torch.zeros(T, N, 1, device=dev)
         self.returns = torch.zeros(T, N, 1, device=dev)
         self.advantages = torch.zeros(T, N, 1, device=dev)
+        self.storage_rows = torch.zeros(T * N, dtype=torch.int64, device=dev)     # fixed address: captured CUDA graphs read it
         self.reset()
 
     def reset(self):
         self.step = self.pos = 0
         self.full = self.generator_ready = False
-        self.indices = np.random.permutation(self.buffer_size * self.n_envs)      # buffers.py:673, one per rollout
-        # storage row (t*N + n) of the reference's env-major flat index i = n*T + t
-        i = torch.from_numpy(self.indices)
-        self.storage_rows = ((i % self.buffer_size) * self.n_envs + i // self.buffer_size).to(self.device)
+        self.set_permutation(np.random.permutation(self.buffer_size * self.n_envs))    # buffers.py:673, one per rollout
+
+    def set_permutation(self, indices):
+        """`indices`: a permutation of the reference's env-major flat index i = n*T + t (swap_and_flatten order); the
+        storage row of i is t*N + n."""
+        self.indices = np.asarray(indices)
+        i = torch.from_numpy(self.indices).long()
+        self.storage_rows.copy_((i % self.buffer_size) * self.n_envs + i // self.buffer_size)
 
     def add(self, obs, action, reward, episode_start, value, log_prob):
         if isinstance(episode_start, np.ndarray):

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <mutex>
 
 namespace gnbv {
 static thread_local char g_err[512] = "";
@@ -28,6 +29,27 @@ static int env_mode(const char* name, int dflt) {
 int conv2_tc_mode() { static const int m = env_mode("GNBV_CONV2_TC", 30); return m; }
 int conv1_mma_mode() { static const int m = env_mode("GNBV_CONV1_MMA", 3); return m; }
 int gemm_mma_mode() { static const int m = env_mode("GNBV_GEMM_MMA", 1); return m; }
+}  // namespace gnbv
+
+namespace gnbv {
+// (kernel, device) -> largest dynamic shared-memory size already granted
+int ensure_dyn_smem_impl(const void* func, size_t bytes) {
+    struct Entry { const void* f; int dev; size_t bytes; };
+    static Entry table[256];
+    static int used = 0;
+    static std::mutex mu;
+    int dev = 0;
+    GNBV_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    Entry* e = nullptr;
+    for (int i = 0; i < used; ++i)
+        if (table[i].f == func && table[i].dev == dev) { e = &table[i]; break; }
+    if (e && e->bytes >= bytes) return GNBV_OK;
+    GNBV_CUDA_CHECK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (!e && used < 256) { e = &table[used++]; e->f = func; e->dev = dev; }
+    if (e) e->bytes = bytes;
+    return GNBV_OK;
+}
 }  // namespace gnbv
 
 extern "C" int gnbv_kernel_mode(int which) {

@@ -44,6 +44,12 @@ int gemm_mma_mode();      // GNBV_GEMM_MMA
         }                                                                                  \
     } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of before every launch: the driver
+// call costs microseconds on the host, and a minibatch update issues dozens of launches.  Grows monotonically.
+int ensure_dyn_smem_impl(const void* func, size_t bytes);
+template <typename F>
+static inline int ensure_dyn_smem(F* func, size_t bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void*>(func), bytes); }
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float warp_sum(float v) {

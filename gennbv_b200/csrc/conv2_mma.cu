@@ -690,7 +690,7 @@ int conv2_mma_items(int B, int G2) { return B * conv2_mma_chunks(G2); }
 int launch_conv2_fwd_mma(const float* y1, const float* stat1, const float* w, const float* bias, float* y2, float* part,
                          int B, int G1, int G2, cudaStream_t stream) {
     // set on every launch (a host call of about a microsecond): the attribute is per device, and a process may drive several
-    GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+    { int rc_ = ensure_dyn_smem(conv2_fwd_mma_kernel, MMA_SMEM); if (rc_) return rc_; }
     const int chunks = conv2_mma_chunks(G2), items = B * chunks;
     int sms = 148;
     const int grid = std::min(items, sms * 3);
@@ -707,7 +707,7 @@ int conv2_dgrad_mma_items_per_sample(int G1) {
 
 int launch_conv2_dgrad_mma(const float* dy2cl, const float* w, const float* y1, const float* stat1, float* g1, float* bpart,
                            int B, int G1, int G2, cudaStream_t stream) {
-    GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_dgrad_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MMA_SMEM));
+    { int rc_ = ensure_dyn_smem(conv2_dgrad_mma_kernel, MMA_SMEM); if (rc_) return rc_; }
     const int ips = conv2_dgrad_mma_items_per_sample(G1), items = B * ips;
     conv2_dgrad_mma_kernel<<<std::min(items, 148 * 3), MMA_THREADS, MMA_SMEM, stream>>>(dy2cl, w, y1, stat1, g1, bpart, G1, G2, ips, items);
     GNBV_LAUNCH_CHECK("conv2_dgrad_mma_kernel");
@@ -726,7 +726,7 @@ int launch_conv2_wgrad_staged(const float* y1, const float* stat1, const float* 
     const int LP = pad_mod32(G1 * C, 4), DP = pad_mod32(G2 * C, 8);
     const size_t smem = (size_t)2 * (27 * LP + WGS_ROWS * DP) * 4;
     GNBV_REQUIRE(smem <= 200 * 1024, "conv2 wgrad: grid too large for the staged kernel's shared-memory lines");
-    GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_dyn_smem(conv2_wgrad_staged_kernel, smem); if (rc_) return rc_; }
     const int total = B * G2 * (int)ceil_div(G2, WGS_ROWS);
     const int want = std::min(std::min(max_blocks, 148), total);
     const int gpb = (int)ceil_div(total, want), nblk = (int)ceil_div(total, gpb);

@@ -209,7 +209,7 @@ int launch_conv2_fwd_tc(const float* y1, const float* stat1, const float* w, con
                         int* err, int B, int G1, int G2, cudaStream_t stream) {
     GNBV_REQUIRE(conv2_tc_supported(G1, G2), "conv2_fwd_tc: unsupported grid (G1=%d G2=%d)", G1, G2);
     const int RT = rows_per_tile(G2), tiles = conv2_tc_tiles(B, G2);
-    GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2T_SMEM));
+    { int rc_ = ensure_dyn_smem(conv2_fwd_tc_kernel, C2T_SMEM); if (rc_) return rc_; }
     const int grid = std::min(tiles, 148);
     conv2_fwd_tc_kernel<<<grid, C2T_THREADS, C2T_SMEM, stream>>>(y1, stat1, w, bias, y2, part, err, G1, G2, RT, tiles);
     GNBV_LAUNCH_CHECK("conv2_fwd_tc_kernel");

@@ -18,6 +18,7 @@
 #include "conv2_mma.cuh"
 #include "mma.cuh"
 #include "tma.cuh"
+#include "encoder.cuh"
 
 #include <stdlib.h>
 
@@ -163,7 +164,8 @@ __device__ __forceinline__ void chan_merge(double& n, double& mean, double& M2, 
 __global__ void __launch_bounds__(32 * C1)
 bn_finalize_kernel(const float* __restrict__ part, int nblk, const float* __restrict__ gamma,
                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
-                   int64_t* __restrict__ num_batches_tracked, float* __restrict__ stat, float eps, float momentum) {
+                   int64_t* __restrict__ num_batches_tracked, float* __restrict__ stat, float eps, float momentum,
+                   const int64_t* __restrict__ freeze) {
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double n = 0, mean = 0, M2 = 0;
     for (int k = lane; k < nblk; k += 32) {
@@ -188,7 +190,9 @@ bn_finalize_kernel(const float* __restrict__ part, int nblk, const float* __rest
     stat[1 * C1 + c] = invstd;
     stat[2 * C1 + c] = a;
     stat[3 * C1 + c] = beta[c] - (float)mean * a;
-    if (running_mean) {
+    // `freeze` (device flag, may be null): a set flag leaves the running statistics alone -- the PPO update's sticky
+    // KL-stop flag, so that minibatches enqueued after the stop change no state (ppo_update.cu)
+    if (running_mean && !(freeze && *freeze != 0)) {
         double unbiased = n > 1 ? M2 / (n - 1) : var;
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
@@ -1557,11 +1561,10 @@ extern "C" size_t gnbv_encoder_workspace_bytes(int batch, int grid_size, int sta
     return make_ws(d, with_backward != 0).total * 4 + 256;
 }
 
-extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
-                                    const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
-                                    float* features, void* workspace,
-                                    size_t workspace_bytes, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
+                                const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                                float* features, void* workspace, size_t workspace_bytes, const int64_t* freeze,
+                                cudaStream_t stream) {
     GNBV_REQUIRE(p && obs && features && workspace, "gnbv_encoder_forward: null pointer argument");
     GNBV_REQUIRE(batch > 0 && grid_size >= 7 && state_dim > 0 && state_dim % 6 == 0,
                  "gnbv_encoder_forward: bad sizes (batch=%d grid=%d state=%d)", batch, grid_size, state_dim);
@@ -1602,11 +1605,11 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
         const int total_rb = B * d.nrb1;
         const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, 1184));
         if (conv1_mma_mode() & 1) {
-            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c1));
+            { int rc_ = ensure_dyn_smem(conv1_fwd_mma_kernel, smem_c1); if (rc_) return rc_; }
             conv1_fwd_mma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), C1M_THREADS, smem_c1, stream>>>(
                 obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
         } else {
-            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c1));
+            { int rc_ = ensure_dyn_smem(conv1_fwd_tma_kernel, smem_c1); if (rc_) return rc_; }
             conv1_fwd_tma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), CONV1_THREADS, smem_c1, stream>>>(
                 obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
         }
@@ -1622,7 +1625,7 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
         const int nm = (int)ceil_div((int64_t)nrec1, MERGE_FAN);
         bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part1, nrec1, ws + w.merge1);
         bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.merge1, nm, p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, p->bn1_nbt,
-                                                      ws + w.stat1, 1e-5f, 0.1f);
+                                                      ws + w.stat1, 1e-5f, 0.1f, freeze);
     }
     else
         bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn1_w, p->bn1_b, p->bn1_rm, p->bn1_rv, ws + w.stat1, 1e-5f);
@@ -1656,7 +1659,7 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
         const int nm = (int)ceil_div((int64_t)nrec2, MERGE_FAN);
         bn_merge_kernel<<<nm, 32 * C1, 0, stream>>>(part2, nrec2, ws + w.merge2);
         bn_finalize_kernel<<<1, 32 * C1, 0, stream>>>(ws + w.merge2, nm, p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, p->bn2_nbt,
-                                                      ws + w.stat2, 1e-5f, 0.1f);
+                                                      ws + w.stat2, 1e-5f, 0.1f, freeze);
     }
     else
         bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, ws + w.stat2, 1e-5f);
@@ -1679,12 +1682,27 @@ extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* o
     return rc;
 }
 
+extern "C" int gnbv_encoder_forward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
+                                    const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                                    float* features, void* workspace, size_t workspace_bytes, void* stream) {
+    return encoder_forward_impl(p, obs, obs_row_stride, row_index, batch, grid_size, state_dim, training, features, workspace,
+                                workspace_bytes, nullptr, (cudaStream_t)stream);
+}
+
 extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
                                      const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
-                                     const float* features,
-                                     const float* dfeatures, const gnbv_encoder_grads* gr, void* workspace,
-                                     size_t workspace_bytes, void* stream_) {
+                                     const float* features, const float* dfeatures, const gnbv_encoder_grads* gr,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+    return gnbv_encoder_backward_phase(p, obs, obs_row_stride, row_index, batch, grid_size, state_dim, training, features,
+                                       dfeatures, gr, workspace, workspace_bytes, GNBV_BWD_ALL, stream);
+}
+
+extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,
+                                           const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                                           const float* features, const float* dfeatures, const gnbv_encoder_grads* gr,
+                                           void* workspace, size_t workspace_bytes, int phases, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    GNBV_REQUIRE(phases & GNBV_BWD_ALL, "gnbv_encoder_backward_phase: empty phase mask");
     GNBV_REQUIRE(p && obs && features && dfeatures && gr && workspace, "gnbv_encoder_backward: null pointer argument");
     GNBV_REQUIRE(gr->conv1_w && gr->conv1_b && gr->bn1_w && gr->bn1_b && gr->conv2_w && gr->conv2_b && gr->bn2_w && gr->bn2_b &&
                      gr->grid_fc_w && gr->grid_fc_b && gr->act_fc1_w && gr->act_fc1_b && gr->act_fc2_w && gr->act_fc2_b &&
@@ -1699,6 +1717,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     GemmEpilogue none;
     int rc;
     auto blocks = [](int64_t n) { return (unsigned)ceil_div(n, 256); };
+    if (phases & GNBV_BWD_LINEAR) {
     stage_mark(GNBV_ST_BWD_LINEAR, stream);
     // ---- fuse layer: features = relu(cat W^T + b)
     relu_mask_kernel<<<blocks((int64_t)B * d.FEAT), 256, 0, stream>>>(dfeatures, d.FEAT, ws + w.dz, d.FEAT, features, d.FEAT, B, d.FEAT);
@@ -1728,6 +1747,8 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     rc = launch_gemm(dcat_g, 2 * H, 1, p->grid_fc_w, d.flat2, 1, ws + w.dact2, d.flat2, B, (int)d.flat2, H, none, ws + w.gemm, stream);
     if (rc) return rc;
     GNBV_LAUNCH_CHECK("linear backward");
+    }
+    if (!(phases & GNBV_BWD_CONV)) return GNBV_OK;
     // ---- BN2 + ReLU backward
     stage_mark(GNBV_ST_BWD_BN2, stream);
     bn2_bwd_reduce_kernel<<<dim3(C1, B), 256, 0, stream>>>(ws + w.dact2, ws + w.act2, ws + w.y2, ws + w.stat2, ws + w.bn2part, d.P2);
@@ -1741,7 +1762,7 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
     const size_t line_f = (size_t)((d.G1 * C1 + 31) / 32) * 32, dyl_f = (size_t)((d.G2 * C1 + 31) / 32) * 32;
     const size_t smem_wg2 = std::max(3 * (size_t)WG2_REC, 2 * (9 * line_f + dyl_f)) * 4;
     GNBV_REQUIRE(smem_wg2 <= 200 * 1024, "gnbv_encoder_backward: grid too large for the conv2 wgrad staging buffers");
-    GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv2_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg2));
+    { int rc_ = ensure_dyn_smem(conv2_wgrad_kernel, smem_wg2); if (rc_) return rc_; }
     int nrec_wg2 = w.nblk_wg2;
     if (conv2_tc_mode() & 16) {
         rc = launch_conv2_wgrad_staged(ws + w.y1, ws + w.stat1, ws + w.dy2cl, ws + w.wg2part, B, d.G1, d.G2, w.nblk_wg2, &nrec_wg2, stream);
@@ -1784,13 +1805,13 @@ extern "C" int gnbv_encoder_backward(const gnbv_encoder_params* p, const float* 
         const int nyb = (int)ceil_div(d.G1, WG1_RB), total_rb = B * d.G1 * nyb;
         const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, w.nblk_wg1));
         int nblk = (int)ceil_div(total_rb, rbpb);                // <= w.nblk_wg1: the partial buffer is large enough
-        GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_wg1));
+        { int rc_ = ensure_dyn_smem(conv1_wgrad_tma_kernel, smem_wg1); if (rc_) return rc_; }
         if (conv1_mma_mode() & 2) {
             const int nyb_m = (int)ceil_div(d.G1, WG1M_RB), total_m = B * d.G1 * nyb_m;
             const int rbpb_m = (int)std::max<int64_t>(1, ceil_div(total_m, w.nblk_wg1));
             const int nblk_m = (int)ceil_div(total_m, rbpb_m);
             const size_t smem_m = (size_t)2 * (3 * (2 * WG1M_RB + 1) * d.G + 2 * WG1M_RB * d.G1 * C1) * 4;
-            GNBV_CUDA_CHECK(cudaFuncSetAttribute(conv1_wgrad_mma_kernel<WG1M_RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_m));
+            { int rc_ = ensure_dyn_smem(conv1_wgrad_mma_kernel<WG1M_RB>, smem_m); if (rc_) return rc_; }
             conv1_wgrad_mma_kernel<WG1M_RB><<<nblk_m, C1M_THREADS, smem_m, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1,
                                                                                      ws + w.y1, ws + w.stat1, ws + w.coef1, ws + w.wg1part,
                                                                                      d.G, d.G1, total_m, rbpb_m);

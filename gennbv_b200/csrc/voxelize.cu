@@ -487,7 +487,7 @@ extern "C" int gnbv_scan_raycast(const float* depth, const int32_t* seg, const f
     if (rc) return rc;
     const size_t smem = (size_t)(2 * L.words + LIST_CAP) * 4;
     GNBV_REQUIRE(smem <= 200 * 1024, "gnbv_scan_raycast: grid_size %d needs %zu B of shared memory (max G = 92)", G, smem);
-    GNBV_CUDA_CHECK(cudaFuncSetAttribute(scan_raycast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { int rc_ = ensure_dyn_smem(scan_raycast_kernel, smem); if (rc_) return rc_; }
     uint32_t* tmask = reinterpret_cast<uint32_t*>((char*)workspace + L.off_tmask);
     uint32_t* rmask = reinterpret_cast<uint32_t*>((char*)workspace + L.off_rmask);
     const int vec_in = ((H * W) % 4 == 0) && (((uintptr_t)depth | (uintptr_t)seg) & 15) == 0;

@@ -28,6 +28,34 @@ def allreduce_mean_(flat: torch.Tensor):
     return flat
 
 
+def allreduce_avg_(t: torch.Tensor):
+    """In-place average over ranks, as one collective: NCCL reduces with AVG; gloo (CPU tests) has no AVG, so SUM and
+    scale.  Enqueued on the CURRENT stream's NCCL work queue (call it under `torch.cuda.stream(side)` to overlap)."""
+    rank, ws = world()
+    if ws > 1:
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.mul_(1.0 / ws)
+    return t
+
+
+def require_equal(value: int, what: str):
+    """Raises on every rank if `value` differs across ranks (e.g. rollout sizes: unequal minibatch counts would leave the
+    per-minibatch gradient all-reduces unmatched and hang the job)."""
+    rank, ws = world()
+    if ws > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        lo = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+        hi = lo.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if int(lo) != int(hi):
+            raise RuntimeError(f"{what} differs across ranks ({int(lo)} .. {int(hi)}): every rank must run the same number of "
+                               "minibatches per epoch; use equal env shards")
+
+
 def consensus_max(x: torch.Tensor):
     """MAX over ranks -- used for approx_kl so that the KL early stop of ppo_grid_obs.py:264-268 is taken by every rank
     at the same minibatch (a rank-local `break` would dead-lock the next gradient all-reduce)."""
@@ -52,3 +80,31 @@ def broadcast_state_(flat_params: torch.Tensor, buffers):
         dist.broadcast(flat_params, 0)
         for b in buffers:
             dist.broadcast(b, 0)
+
+
+class OverlappedGradAllreduce:
+    """The per-minibatch gradient all-reduce (mean) of the flat bucket `[vote slot | conv tensors | Linear tensors]`
+    (gennbv_b200/policy.py) in two pieces: `start_linear()` right after the Linear phase of the backward -- it runs on a
+    side stream under the convolution backward and carries 99.9 % of the bytes -- and `finish()` after the conv phase: the
+    remaining ~30 KB (votes + conv tensors) on the caller's stream, then the join."""
+
+    def __init__(self, bucket: torch.Tensor, split: int):
+        self.big, self.small = bucket[split:], bucket[:split]
+        self.stream = None
+
+    def start_linear(self):
+        if world()[1] == 1:
+            return
+        main = torch.cuda.current_stream()
+        if self.stream is None:
+            self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(main)
+        with torch.cuda.stream(self.stream):
+            allreduce_avg_(self.big)
+
+    def finish(self):
+        if world()[1] == 1:
+            return
+        allreduce_avg_(self.small)
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)

@@ -152,19 +152,18 @@ class Hybrid_Encoder(nn.Module):
         _lib.check(rc, "gnbv_encoder_forward")
         return feats
 
-    def _run_backward(self, obs, feats, dfeat, batch, ctx_training=True, ws=None, row_index=None, grads=None):
+    def _run_backward(self, obs, feats, dfeat, batch, ctx_training=True, ws=None, row_index=None, grads=None, phases=3):
         grads = [torch.empty_like(p) for p in self._param_list()] if grads is None else grads
         gp = _lib.EncoderGrads()
         for name, g in zip(_lib.EncoderGrads.FIELDS, grads):
             setattr(gp, name, g.data_ptr())
         p = self._c_params()
         ws = self._ws if ws is None else ws
-        rc = _lib.lib().gnbv_encoder_backward(ctypes.byref(p), obs.data_ptr(), obs.stride(0),
-                                              None if row_index is None else row_index.data_ptr(), batch, self.grid_size,
-                                              self.state_dim, int(ctx_training), feats.data_ptr(), dfeat.data_ptr(),
-                                              ctypes.byref(gp),
-                                              ws.data_ptr(), ws.numel(), ops._stream())
-        _lib.check(rc, "gnbv_encoder_backward")
+        rc = _lib.lib().gnbv_encoder_backward_phase(ctypes.byref(p), obs.data_ptr(), obs.stride(0),
+                                                    None if row_index is None else row_index.data_ptr(), batch, self.grid_size,
+                                                    self.state_dim, int(ctx_training), feats.data_ptr(), dfeat.data_ptr(),
+                                                    ctypes.byref(gp), ws.data_ptr(), ws.numel(), int(phases), ops._stream())
+        _lib.check(rc, "gnbv_encoder_backward_phase")
         return grads
 
     def forward(self, observations):

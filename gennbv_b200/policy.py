@@ -115,7 +115,12 @@ class ActorCriticPolicy_Train_Eval(nn.Module):
         offs = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])    # 16-byte aligned slices
         dev = order[0].device
         self.flat_params = torch.zeros(int(offs[-1]), device=dev)
-        self.flat_grads = torch.zeros(int(offs[-1]), device=dev)
+        # gradient bucket = [vote slot (4 floats, 16 B) | flat gradients]: the data-parallel all-reduce carries the KL-stop
+        # votes of the ranks in the same (small, conv-side) message as the gradients (csrc/ppo_update.cu)
+        self.grad_bucket = torch.zeros(4 + int(offs[-1]), device=dev)
+        self.grad_vote = self.grad_bucket[0:1]
+        self.flat_grads = self.grad_bucket[4:]
+        self._arena_order = order
         self._arena = []
         for p, o, n in zip(order, offs[:-1], sizes):
             view = self.flat_params[o:o + n].view_as(p)
@@ -132,6 +137,23 @@ class ActorCriticPolicy_Train_Eval(nn.Module):
         assert self._arena[-1][0] == o_b + A
         self.head_w_grad = self.flat_grads[o_w:o_w + (A + 1) * F].view(A + 1, F)
         self.head_b_grad = self.flat_grads[o_b:o_b + A + 1]
+
+    def arena_parameters(self):
+        """The parameters in flat-arena order (`_arena[i]` = (offset, numel) of the i-th)."""
+        return list(self._arena_order)
+
+    def optimizer_parameter_order(self):
+        return list(self.parameters())                      # the order torch.optim indexes `state` by
+
+    def optimizer_arena_order(self):
+        where = {id(p): on for p, on in zip(self._arena_order, self._arena)}
+        return [where[id(p)] for p in self.parameters()]
+
+    @property
+    def linear_slice_offset(self):
+        """First element of `flat_grads` that belongs to a Linear layer (grid_fc.weight): everything from here on is final
+        after the Linear phase of the backward, the conv tensors before it only after the conv phase."""
+        return self._arena[8][0]
 
     def encoder_grad_views(self):
         """Views of the flat gradient arena for the encoder's 16 tensors, in gnbv_encoder_grads order (independent of

@@ -63,24 +63,53 @@ class ReplaySensor(SensorSource):
 class FrameListSensor(SensorSource):
     """Cycles through pre-rendered frames (dicts with depth / seg / rgba / c2w).  With `host=True` the frames live in
     pinned host memory and every render() issues the host->device copies on the current stream -- the shape of a real
-    deployment where the simulator hands over host or foreign-device buffers."""
+    deployment where the simulator hands over host or foreign-device buffers.
+
+    `prefetch_next()` (host frames only) starts the copy of the NEXT frame on a side stream into the second of two device
+    frame sets; the following render() then only waits for that copy.  Causality of the RL loop is the caller's business:
+    the next frame exists once the next action has been chosen, i.e. after the policy forward on the current observation,
+    so a training step calls it between its forward and its backward and the copy hides under the backward."""
 
     def __init__(self, frames, device, host=False):
         self.device, self.host, self.t = torch.device(device), host, 0
         keys = ("depth", "seg", "rgba", "c2w")
         if host:
             self.frames = [{k: f[k].cpu().pin_memory() for k in keys if f.get(k) is not None} for f in frames]
-            self.dev = {k: torch.empty_like(v, device=self.device) for k, v in self.frames[0].items()}
+            self.dev = [{k: torch.empty_like(v, device=self.device) for k, v in self.frames[0].items()} for _ in range(2)]
+            self._copy_stream = None
+            self._ready = [None, None]             # event of an in-flight prefetch into set i, for frame index _ready_t[i]
+            self._ready_t = [-1, -1]
         else:
             self.frames = [{k: f[k].to(self.device).contiguous() for k in keys if f.get(k) is not None} for f in frames]
         self.height, self.width = self.frames[0]["depth"].shape[-2:]
         self.bytes_per_frame = sum(v.numel() * v.element_size() for v in self.frames[0].values())
 
+    def prefetch_next(self):
+        if not self.host:
+            return
+        t, main = self.t, torch.cuda.current_stream(self.device)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        s = t % 2
+        # set s was last read by the kernels of step t-2, all enqueued on `main` before this call
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in self.frames[t % len(self.frames)].items():
+                self.dev[s][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._ready[s], self._ready_t[s] = ev, t
+
     def render(self, poses):
-        f = self.frames[self.t % len(self.frames)]
+        t = self.t
+        f = self.frames[t % len(self.frames)]
         self.t += 1
         if self.host:
-            for k, v in f.items():
-                self.dev[k].copy_(v, non_blocking=True)
-            f = self.dev
+            s = t % 2
+            if self._ready_t[s] == t:
+                torch.cuda.current_stream(self.device).wait_event(self._ready[s])
+            else:
+                for k, v in f.items():
+                    self.dev[s][k].copy_(v, non_blocking=True)
+            f = self.dev[s]
         return SensorFrame(depth=f["depth"], seg=f["seg"], rgba=f.get("rgba"), c2w=f["c2w"])

@@ -27,7 +27,7 @@ extern "C" {
 #define GNBV_E_CUDA (-2)     /* a CUDA runtime call / kernel launch failed */
 #define GNBV_E_WORKSPACE (-3) /* workspace too small */
 
-#define GNBV_ABI_VERSION 1
+#define GNBV_ABI_VERSION 2
 
 int gnbv_abi_version(void);
 /* Kernel variants in effect for this process: which = 0 -> GNBV_CONV2_TC, 1 -> GNBV_CONV1_MMA, 2 -> GNBV_GEMM_MMA
@@ -230,6 +230,19 @@ int gnbv_encoder_backward(const gnbv_encoder_params* params, const float* obs, i
                           const float* features, const float* dfeatures, const gnbv_encoder_grads* grads,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same backward in two phases, so that a data-parallel caller can start the all-reduce of the large gradient slice
+ * while the convolution backward still runs (the flat gradient arena of gennbv_b200/policy.py is ordered conv tensors
+ * first): GNBV_BWD_LINEAR computes the gradients of out_fc, act_fc1/2 and grid_fc (final after this phase) and the
+ * gradient entering the conv stack; GNBV_BWD_CONV (must follow, same workspace) computes bn2, conv2, bn1, conv1.
+ * gnbv_encoder_backward == phases GNBV_BWD_ALL. */
+#define GNBV_BWD_LINEAR 1
+#define GNBV_BWD_CONV 2
+#define GNBV_BWD_ALL 3
+int gnbv_encoder_backward_phase(const gnbv_encoder_params* params, const float* obs, int64_t obs_row_stride,
+                                const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
+                                const float* features, const float* dfeatures, const gnbv_encoder_grads* grads,
+                                void* workspace, size_t workspace_bytes, int phases, void* stream);
+
 /* ---- actor / critic heads + MultiCategorical distribution + PPO loss + optimizer ---- */
 
 /* action_net Linear(256, sum(nvec)) and value_net Linear(256,1) (stable_baselines3/common/policies.py:984,994,
@@ -273,6 +286,51 @@ int gnbv_grad_norm(const float* grads, int64_t n, double max_norm, float* worksp
 int gnbv_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                    const float* clip_workspace, double lr, double beta1, double beta2, double eps, int64_t step,
                    double grad_scale, void* stream);
+
+/* ---- one PPO minibatch update as a fixed launch sequence (CUDA-graph capturable, no host decision inside) ----
+ * Replaces the body of the minibatch loop of PPO_Grid_Obs.train (stable_baselines3/ppo/ppo_grid_obs.py:201-275) together
+ * with RolloutBuffer._get_samples (stable_baselines3/common/buffers.py:753-762):
+ *   gnbv_ppo_minibatch_grads : gather the minibatch rows (device cursor ctl[0] into storage_rows), evaluate_actions in
+ *       training mode, loss forward + backward, all parameter gradients (enc_grads, head_*_grad), scalars, KL vote;
+ *       `phases` as in gnbv_encoder_backward_phase (GNBV_BWD_LINEAR also does everything up to the loss);
+ *   gnbv_ppo_minibatch_apply : sticky KL-stop decision from the (all-reduced) vote, log row, clip_grad_norm_ + Adam on the
+ *       flat arenas, cursor++.  While the stop flag ctl[1] is set nothing changes state (Adam, BN running statistics, log).
+ * ctl (device int64[8], zeroed by the caller at the start of an epoch except ctl[2] and ctl[3] = -1 at the start of train()):
+ *   [0] minibatch cursor of the epoch, [1] stop flag, [2] Adam step count, [3] cursor at which the stop was raised,
+ *   [4] number of log rows written.
+ * vote: device float the caller places right behind the flat gradient bucket so that ONE all-reduce(sum) carries gradients
+ *   and the stop decision of all ranks (1.0 = this rank's approx_kl > 1.5 target_kl; target_kl < 0 disables the test).
+ * log: [log_capacity, 8] floats, row k = scalars of the k-th executed minibatch (layout of gnbv_ppo_loss). */
+typedef struct gnbv_ppo_minibatch {
+    const gnbv_encoder_params* enc;          /* host struct of device pointers */
+    const gnbv_encoder_grads* enc_grads;
+    const float *head_w, *head_b;            /* [A+1, feat_dim], [A+1]: action_net | value_net */
+    float *head_w_grad, *head_b_grad;
+    const int* nvec;                         /* host */
+    int num_sub, feat_dim;
+    const float* observations;               /* rollout storage, row = t*N + n */
+    int64_t obs_row_stride;
+    const float *actions, *values, *log_probs, *advantages, *returns;   /* [rows, num_sub] f32, [rows] f32 x4 */
+    const int64_t* storage_rows;             /* the rollout's permutation mapped to storage rows */
+    int64_t rows_base;                       /* minibatch k reads storage_rows[rows_base + k*batch .. + batch), k = ctl[0] */
+    int batch, grid_size, state_dim, normalize_advantage;
+    double clip_range, clip_range_vf, ent_coef, vf_coef, pg_coef, target_kl;
+    int64_t* ctl;
+    float* vote;
+    float* log;
+    int64_t log_capacity;
+    void* enc_workspace;                     /* gnbv_encoder_workspace_bytes(batch, grid, state, 1) */
+    size_t enc_workspace_bytes;
+    void* mb_workspace;                      /* gnbv_ppo_minibatch_workspace_bytes(...) */
+    size_t mb_workspace_bytes;
+} gnbv_ppo_minibatch;
+size_t gnbv_ppo_minibatch_workspace_bytes(int batch, int num_logits, int num_sub, int feat_dim);
+size_t gnbv_ppo_apply_workspace_bytes(void);
+int gnbv_ppo_minibatch_grads(const gnbv_ppo_minibatch* args, int phases, void* stream);
+int gnbv_ppo_minibatch_scalars(const gnbv_ppo_minibatch* args, const float** scalars);   /* device pointer to float[8] */
+int gnbv_ppo_minibatch_apply(const gnbv_ppo_minibatch* args, float* params, const float* grads, float* exp_avg,
+                             float* exp_avg_sq, int64_t n, double max_grad_norm, double lr, double beta1, double beta2,
+                             double eps, double grad_scale, float* apply_workspace, void* stream);
 
 /* Bare fp32 GEMM on device pointers: C[M,N] = relu?(A*B + bias), element strides (see gennbv_b200/csrc/gemm.cuh);
  * replaces the cuBLAS calls behind nn.Linear (hybrid_encoder.py:39-54; policies.py:984,994). */

@@ -23,13 +23,31 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
 
 
-def grad_close(k, got, want, training, scale, rtol=2e-4):
-    """A conv bias followed by train-mode BatchNorm has an exactly-zero gradient: both sides hold rounding noise
-    there, so the comparison is absolute, relative to the layer's weight-gradient scale."""
+def grad_close(k, got, want, training, scale, rtol=RTOL, want64=None):
+    """<= 1e-4 relative (BASELINE.json) per gradient tensor.  `want` is the fp32 oracle (torch CPU); when `want64`, the SAME
+    oracle evaluated in float64, is given, it is the arbiter: the kernel must be within rtol of the float64 value, and
+    within rtol + (the fp32 oracle's own measured rounding error) of the fp32 value -- two fp32 evaluations of a 10^5..10^7
+    term reduction differ from each other by more than either differs from the exact result.
+    A conv bias followed by train-mode BatchNorm has an exactly-zero gradient: both sides hold rounding noise there, so that
+    comparison is absolute, relative to the layer's weight-gradient scale."""
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     if training and (k.endswith("naive_encoder_grid.0.bias") or k.endswith("naive_encoder_grid.3.bias")):
         return float(np.abs(got - want).max()) < rtol * scale
-    return rel_err(got, want) < rtol
+    if want64 is None:
+        return rel_err(got, want) < rtol
+    want64 = np.asarray(want64, np.float64)
+    return rel_err(got, want64) < rtol and rel_err(got, want) < rtol + rel_err(want, want64)
+
+
+def oracle_grads(ref, obs, wsum, training, dtype):
+    """Features, parameter gradients of sum(features * wsum) and BN buffers of a COPY of `ref` evaluated in `dtype`."""
+    import copy
+    m = copy.deepcopy(ref.features_extractor).to(dtype)
+    m.train(training)
+    m.zero_grad()
+    f = m(obs.to(dtype))
+    (f * wsum.to(dtype)).sum().backward()
+    return f.detach(), {k: p.grad.detach() for k, p in m.named_parameters()}, {k: b.detach().clone() for k, b in m.named_buffers()}
 
 
 def make_policy(G, seed, state_dim=600):
@@ -80,7 +98,7 @@ def test_policy_matches_reference_golden_g20():
     """Forward (eval + train BN), log_prob / entropy / values, PPO loss, every gradient, clip norm and the Adam step
     against tests/golden/policy_g20.npz (written by the reference's own modules)."""
     gd = np.load(os.path.join(GOLDEN_DIR, "policy_g20.npz"))
-    pol, _, D = make_policy(20, int(gd["seed"]))
+    pol, ref, D = make_policy(20, int(gd["seed"]))
     obs = golden_obs().to(DEV)
     actions = torch.from_numpy(gd["actions"]).to(DEV)
     pol.set_training_mode(False)
@@ -101,13 +119,26 @@ def test_policy_matches_reference_golden_g20():
     pol.optimizer.zero_grad()
     loss.backward()
     scale = float(np.abs(gd["grad.features_extractor.naive_encoder_grid.0.weight"]).max())
+    # float64 arbiter: PolicyRef is bit-equal to the reference's modules in fp32 (tests/test_encoder_ref_vs_reference.py);
+    # the same function in float64 measures the rounding error the fp32 golden itself carries.  The golden was recorded
+    # after two train-mode forwards from the seeded running statistics; gradients do not depend on the running buffers.
+    import copy
+    ref64 = copy.deepcopy(ref).double().train()
+    T64 = lambda k: torch.from_numpy(gd[k]).double()
+    v64, lp64, ent64 = ref64.evaluate_actions(obs.cpu().double(), actions.cpu())
+    loss64, _ = encoder_ref.ppo_loss(v64, lp64, ent64, T64("old_values"), T64("old_log_prob"), T64("advantages"), T64("returns"))
+    loss64.backward()
+    g64 = {k: p.grad.numpy() for k, p in ref64.named_parameters()}
     for k, p in pol.named_parameters():
         g = p.grad.detach().cpu().numpy()
         if "grad." + k in gd.files:
-            assert grad_close(k, g, gd["grad." + k], True, scale), k
+            assert grad_close(k, g, gd["grad." + k], True, scale, want64=g64[k]), k
         else:
-            flat = g.reshape(-1)
-            assert rel_err(flat[:: max(1, flat.size // 2048)][:2048], gd["grad." + k + ".sample"]) < 2e-4, k
+            flat, f64 = g.reshape(-1), g64[k].reshape(-1)
+            sl = slice(None, None, max(1, flat.size // 2048))
+            want32 = gd["grad." + k + ".sample"]
+            assert rel_err(flat, f64) < RTOL, k
+            assert rel_err(flat[sl][:2048], want32) < RTOL + rel_err(want32, f64[sl][:2048]), k
             assert abs(np.linalg.norm(flat.astype(np.float64)) / float(gd["grad." + k + ".norm"]) - 1) < 1e-4, k
     for k, b in pol.named_buffers():
         assert rel_err(b.detach().cpu().numpy().astype(np.float64), gd["buf." + k]) < RTOL, k
@@ -126,7 +157,9 @@ def test_policy_matches_reference_golden_g20():
             assert float(np.abs((new - before[k].cpu().numpy()) - delta_ref).max()) <= 2e-3 * 1e-4 + 1e-9, k
 
 
-@pytest.mark.parametrize("G,B,seed", [(20, 9, 1), (32, 5, 2), (64, 3, 3), (21, 4, 4)])
+# (64, 128) and (64, 256) are the shapes PPO_Grid_Obs.train and bench.py actually run (BASELINE configs[1] / [2]): the
+# persistent-block / work-item splitting of every conv kernel depends on B
+@pytest.mark.parametrize("G,B,seed", [(20, 9, 1), (32, 5, 2), (64, 3, 3), (21, 4, 4), (64, 128, 5), (64, 256, 6)])
 def test_encoder_forward_backward_vs_torch(G, B, seed):
     pol, ref, D = make_policy(G, seed)
     g = torch.Generator().manual_seed(seed)
@@ -135,24 +168,25 @@ def test_encoder_forward_backward_vs_torch(G, B, seed):
     obs[:, 600:600 + G ** 3] = torch.randint(-1, 2, (B, G ** 3), generator=g).float()
     obs[:, 600 + G ** 3:] = torch.rand(B, 8192, generator=g) * 255
     wsum = torch.randn(B, 256, generator=g)
+    obs_d = obs.to(DEV)
+    enc = pol.features_extractor
     for training in (False, True):
-        ref.train(training); pol.train(training)
-        ref.zero_grad()
-        f_ref = ref.features_extractor(obs)
-        (f_ref * wsum).sum().backward()
-        enc = pol.features_extractor
+        f_ref, g32, b32 = oracle_grads(ref, obs, wsum, training, torch.float32)
+        f64, g64, b64 = oracle_grads(ref, obs, wsum, training, torch.float64)
+        pol.train(training)
         for p in enc.parameters():
             p.grad = None
-        f = enc(obs.to(DEV))
-        assert rel_err(f.detach().cpu(), f_ref.detach()) < RTOL, f"features training={training}"
+        f = enc(obs_d)
+        assert rel_err(f.detach().cpu(), f_ref) < RTOL, f"features training={training}"
+        assert rel_err(f.detach().cpu(), f64) < RTOL, f"features (float64 oracle) training={training}"
         (f * wsum.to(DEV)).sum().backward()
-        ref_grads = dict(ref.features_extractor.named_parameters())
-        scale = float(ref_grads["naive_encoder_grid.3.weight"].grad.abs().max())
+        scale = float(g32["naive_encoder_grid.3.weight"].abs().max())
         for k, p in enc.named_parameters():
-            assert grad_close(k, p.grad.cpu(), ref_grads[k].grad, training, scale), f"grad {k} training={training}"
+            assert grad_close(k, p.grad.cpu(), g32[k], training, scale, want64=g64[k]), \
+                f"grad {k} training={training}: vs f64 {rel_err(p.grad.cpu(), g64[k]):.2e}, vs f32 {rel_err(p.grad.cpu(), g32[k]):.2e}"
         if training:
             for k, b in enc.named_buffers():
-                assert rel_err(b.cpu().double(), dict(ref.features_extractor.named_buffers())[k].double()) < RTOL, k
+                assert rel_err(b.cpu().double(), b32[k].double()) < RTOL, k
 
 
 def test_multicategorical_sampling_and_mode():

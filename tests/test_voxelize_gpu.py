@@ -173,6 +173,25 @@ def test_full_size_properties():
     assert float((cov / gt.flatten(1).sum(1)).mean()) > 0.05
 
 
+def test_full_size_against_the_c_oracle():
+    """BASELINE config 2 size (256 envs x 128x128 depth x 64^3 grid), 3 consecutive steps on carried state: every output of the
+    kernel pair -- target counts, tri-class grid, prob / scanned grids, coverage sums and both bit-masks -- equals the C oracle's,
+    bit for bit (the oracle needs ~1 s per step here)."""
+    N, H, W, G, S = 256, 128, 128, 64, 8
+    c = synthetic_case(N, H, W, G, S, 77, steps=3)
+    prob_o = np.zeros((N, G, G, G), np.float32); scan_o = np.zeros_like(prob_o)
+    prob_c, scan_c = prob_o.copy(), scan_o.copy()
+    for t, (depth, seg, c2w, xyz) in enumerate(c["frames"]):
+        o = c_oracle.voxelize_step(depth, seg, c["kinv"], c2w, c["range_gt"], c["vs"], xyz, c["grid_gt"], prob_o, scan_o,
+                                   raw_depth=True, want_masks=True)
+        k = cuda_step(depth, seg, c["kinv"], c2w, c["range_gt"], c["vs"], xyz, c["grid_gt"], prob_c, scan_c, True, want_masks=True)
+        for key in ("num_targets", "tri", "cov_sum", "target_mask", "touched_mask"):
+            np.testing.assert_array_equal(k[key], o[key], err_msg=f"{key}, step {t}")
+        np.testing.assert_array_equal(prob_c, prob_o, err_msg=f"prob_grid, step {t}")
+        np.testing.assert_array_equal(scan_c, scan_o, err_msg=f"scanned_gt_grid, step {t}")
+    assert int(o["num_targets"].min()) >= 0 and int(o["num_targets"].max()) > 100
+
+
 def test_reset_grids():
     N, G = 5, 20
     prob = torch.rand(N, G, G, G, device=DEV); scan = torch.rand_like(prob)
