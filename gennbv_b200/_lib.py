@@ -75,6 +75,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnbv_encoder_backward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_void_p]),
+    "gnbv_encoder_workspace_view": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
     "gnbv_encoder_backward_phase": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_int, c_void_p]),
     "gnbv_ppo_minibatch_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),

@@ -584,9 +584,12 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
     // (n-tile nt = warp + 16k <-> tap nt >> 1, channel half nt & 1 = warp & 1: a warp only ever sees one channel half)
     const int hf = warp & 1;
     const float scv = stat1[2 * C + 8 * hf + g], shv = stat1[3 * C + 8 * hf + g];
-    float acc[WGS_NT][4];
+    // acc: the MMA accumulators of ONE group; tot: their running sum over the block's groups, added with ordinary
+    // round-to-nearest FADDs.  The tensor core's fp32 accumulation truncates, so a chain of thousands of MMAs into one
+    // register drifts (measured 5e-4 relative at B = 128 on the conv1 twin of this kernel); 24 MMAs per chain do not.
+    float acc[WGS_NT][4], tot[WGS_NT][4];
 #pragma unroll
-    for (int k = 0; k < WGS_NT; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
+    for (int k = 0; k < WGS_NT; ++k) { tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0.f; }
     float db_lo = 0.f, db_hi = 0.f;
     const int g0 = blockIdx.x * groups_per_block, g1 = min(total_groups, g0 + groups_per_block);
     if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init_fence(); }
@@ -628,6 +631,8 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
         const float* dys = xs + 27 * LP;
         const bool vrow = t < nrows;
         const int tc = min(t, nrows - 1);                   // rows past the grid alias the last valid row (their A is 0)
+#pragma unroll
+        for (int k = 0; k < WGS_NT; ++k) { acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f; }
         for (int zp = 0; zp < nzp; ++zp) {
             const int za = 2 * zp, zb = za + 1;
             const bool vb = zb < G2;
@@ -659,6 +664,8 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < WGS_NT; ++k) { tot[k][0] += acc[k][0]; tot[k][1] += acc[k][1]; tot[k][2] += acc[k][2]; tot[k][3] += acc[k][3]; }
         __syncthreads();                                    // everyone is done with this stage before it is refilled
     }
     if (!ok) { asm volatile("trap;"); }
@@ -671,7 +678,7 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int co = g + 8 * (e >> 1), ci = 8 * hf + 2 * t + (e & 1);
-                out[(co * C + ci) * NTAPS + tap] = acc[k][e];
+                out[(co * C + ci) * NTAPS + tap] = tot[k][e];
             }
         }
     }

@@ -1119,9 +1119,12 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
     const int TL = (2 * RB + 1) * G;                    // floats per staged tri slab
     const int GL = RB * G1 * C1;                        // floats per staged g1 / y1 slab
     const int STAGE = 3 * TL + 2 * GL;
-    float acc[4][4];
+    // acc: MMA accumulators of ONE row block; tot: their running sum over the block's row blocks (round-to-nearest FADDs).
+    // The tensor core's fp32 accumulation truncates: hundreds of MMAs chained into one register drifted to 5e-4 relative
+    // at B = 128 (tests/test_policy_gpu.py, 64^3 x 128); a dozen per chain do not.
+    float acc[4][4], tot[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+    for (int j = 0; j < 4; ++j) { tot[j][0] = tot[j][1] = tot[j][2] = tot[j][3] = 0.f; }
     float dbs[2] = {0.f, 0.f};
     float kc[2][5];                                         // channels g, g + 8: mean, invstd, a1, S1/n, S2/n
 #pragma unroll
@@ -1177,20 +1180,18 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
         const float* ts = dsm + stage * STAGE;
         const float* gs = ts + 3 * TL;
         const float* ys = gs + GL;
-        float keep[4][4], keep_db[2] = {dbs[0], dbs[1]};
+        const float keep_db[2] = {dbs[0], dbs[1]};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) keep[j][e] = acc[j][e];
+        for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
         const uint32_t inexact = conv1_wgrad_mma_rowblock<false>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
         if (__syncthreads_or((int)inexact)) {               // some input value is not a TF32 number: redo with B split
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[j][e] = keep[j][e];
+            for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
             dbs[0] = keep_db[0]; dbs[1] = keep_db[1];
             conv1_wgrad_mma_rowblock<true>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[j][0] += acc[j][0]; tot[j][1] += acc[j][1]; tot[j][2] += acc[j][2]; tot[j][3] += acc[j][3]; }
         __syncthreads();
     }
     if (!ok) { asm volatile("trap;"); }
@@ -1200,7 +1201,7 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int co = g + 8 * (e >> 1), tap = 8 * j + 2 * t + (e & 1);
-            if (tap < TAPS) red[wid][co * TAPS + tap] = acc[j][e];
+            if (tap < TAPS) red[wid][co * TAPS + tap] = tot[j][e];
         }
     {
         float d0 = dbs[0], d1 = dbs[1];
@@ -1559,6 +1560,23 @@ extern "C" size_t gnbv_encoder_workspace_bytes(int batch, int grid_size, int sta
     if (batch <= 0 || grid_size < 7 || state_dim <= 0) return 0;
     EncDims d = make_dims(batch, grid_size, state_dim);
     return make_ws(d, with_backward != 0).total * 4 + 256;
+}
+
+extern "C" int gnbv_encoder_workspace_view(int batch, int grid_size, int state_dim, int which, int64_t* offset_floats,
+                                           int64_t* count) {
+    GNBV_REQUIRE(offset_floats && count && batch > 0 && grid_size >= 7 && state_dim > 0, "gnbv_encoder_workspace_view: bad arguments");
+    EncDims d = make_dims(batch, grid_size, state_dim);
+    EncWs w = make_ws(d, false);
+    const size_t B = batch;
+    switch (which) {
+        case GNBV_WS_Y1: *offset_floats = (int64_t)w.y1; *count = (int64_t)(B * d.P1 * C1); break;
+        case GNBV_WS_STAT1: *offset_floats = (int64_t)w.stat1; *count = 4 * C1; break;
+        case GNBV_WS_Y2: *offset_floats = (int64_t)w.y2; *count = (int64_t)(B * d.flat2); break;
+        case GNBV_WS_STAT2: *offset_floats = (int64_t)w.stat2; *count = 4 * C1; break;
+        case GNBV_WS_ACT2: *offset_floats = (int64_t)w.act2; *count = (int64_t)(B * d.flat2); break;
+        default: GNBV_REQUIRE(false, "gnbv_encoder_workspace_view: unknown view %d", which);
+    }
+    return GNBV_OK;
 }
 
 int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, int64_t obs_row_stride,

@@ -166,6 +166,16 @@ class Hybrid_Encoder(nn.Module):
         _lib.check(rc, "gnbv_encoder_backward_phase")
         return grads
 
+    def saved_activation(self, which, batch, ws=None):
+        """Debug / test view of an activation the last forward left in its workspace (gnbv_encoder_workspace_view):
+        which in {"y1", "stat1", "y2", "stat2", "act2"} -> a float32 tensor view."""
+        ids = {"y1": 0, "stat1": 1, "y2": 2, "stat2": 3, "act2": 4}
+        off, cnt = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(_lib.lib().gnbv_encoder_workspace_view(batch, self.grid_size, self.state_dim, ids[which], ctypes.byref(off),
+                                                          ctypes.byref(cnt)), "gnbv_encoder_workspace_view")
+        ws = self._ws if ws is None else ws
+        return ws[off.value * 4:(off.value + cnt.value) * 4].view(torch.float32)
+
     def forward(self, observations):
         obs = self._check_obs(observations)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):

@@ -215,6 +215,18 @@ int gnbv_encoder_forward(const gnbv_encoder_params* params, const float* obs, in
                          const int64_t* row_index, int batch, int grid_size, int state_dim, int training,
                          float* features, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Test / debug aid: where a saved activation of the last gnbv_encoder_forward lives inside `workspace` (float offset + count):
+ *   GNBV_WS_Y1    conv1 output before BatchNorm1, channels-last [B, G1^3, 16]
+ *   GNBV_WS_STAT1 [4][16]: batch (or running) mean, invstd, a = gamma*invstd, b = beta - mean*a of BatchNorm1; every kernel
+ *                 forms the ReLU input as fmaf(a, y, b), so (a, b, y) determine the ReLU masks exactly
+ *   GNBV_WS_Y2 / GNBV_WS_STAT2 / GNBV_WS_ACT2: the same for layer 2, channel-major [B, 16, G2^3]. */
+#define GNBV_WS_Y1 0
+#define GNBV_WS_STAT1 1
+#define GNBV_WS_Y2 2
+#define GNBV_WS_STAT2 3
+#define GNBV_WS_ACT2 4
+int gnbv_encoder_workspace_view(int batch, int grid_size, int state_dim, int which, int64_t* offset_floats, int64_t* count);
+
 /* Gradient destinations, one per trainable tensor of gnbv_encoder_params (same shapes). */
 typedef struct gnbv_encoder_grads {
     float *conv1_w, *conv1_b, *bn1_w, *bn1_b, *conv2_w, *conv2_b, *bn2_w, *bn2_b;

@@ -39,13 +39,43 @@ def grad_close(k, got, want, training, scale, rtol=RTOL, want64=None):
     return rel_err(got, want64) < rtol and rel_err(got, want) < rtol + rel_err(want, want64)
 
 
-def oracle_grads(ref, obs, wsum, training, dtype):
+def kernel_relu_masks(enc, B):
+    """The ReLU decisions the kernels took in the last forward, reproduced exactly on the host: every kernel forms the ReLU
+    input as fmaf(a, y, b) in fp32; a single rounding never crosses zero, so its sign is the sign of the exact a*y + b,
+    which float64 evaluates without error in the product (24 x 24 bits) and sign-preservingly in the sum."""
+    G1 = (enc.grid_size - 3) // 2 + 1
+    G2 = (G1 - 3) // 2 + 1
+    y1 = enc.saved_activation("y1", B).view(B, G1, G1, G1, 16).double()
+    s1 = enc.saved_activation("stat1", B).view(4, 16).double()
+    m1 = ((y1 * s1[2] + s1[3]) > 0).permute(0, 4, 1, 2, 3).contiguous()               # -> [B,16,G1,G1,G1]
+    y2 = enc.saved_activation("y2", B).view(B, 16, G2, G2, G2).double()
+    s2 = enc.saved_activation("stat2", B).view(4, 16).double()
+    m2 = (y2 * s2[2].view(1, 16, 1, 1, 1) + s2[3].view(1, 16, 1, 1, 1)) > 0
+    return m1.cpu(), m2.cpu()
+
+
+def oracle_grads(ref, obs, wsum, training, dtype, masks=None):
     """Features, parameter gradients of sum(features * wsum) and BN buffers of a COPY of `ref` evaluated in `dtype`."""
     import copy
     m = copy.deepcopy(ref.features_extractor).to(dtype)
     m.train(training)
     m.zero_grad()
-    f = m(obs.to(dtype))
+    if masks is None:
+        f = m(obs.to(dtype))
+    else:
+        # Same network with the two conv-stack ReLUs evaluated as `x * mask` for GIVEN masks: a ReLU whose input is within
+        # fp32 rounding of zero is decided arbitrarily by any fp32 implementation (at B = 128, 64^3 there are 6 x 10^7 of them
+        # per layer and about one such tie per evaluation); its gradient is discontinuous there, so two correct
+        # implementations differ by one unit's whole contribution (~1e-3 of a BatchNorm bias gradient).  With the kernel's
+        # own tie decisions forced, the float64 gradient is the exact reference for what the kernels must produce.
+        o, n, G = obs.to(dtype), obs.shape[0], m.G
+        a = o[:, :m.state_dim].view(n, -1, 6)
+        fa = m.naive_encoder_action(m.positional_encoding(a).view(n, -1))
+        seq = m.naive_encoder_grid
+        x = o[:, m.state_dim:m.state_dim + G ** 3].reshape(n, 1, G, G, G)
+        x = seq[1](seq[0](x)) * masks[0].to(dtype)
+        x = seq[4](seq[3](x)) * masks[1].to(dtype)
+        f = m.output_layer(torch.cat((fa, m.output_layer_grid(x.reshape(n, -1))), dim=-1))
     (f * wsum.to(dtype)).sum().backward()
     return f.detach(), {k: p.grad.detach() for k, p in m.named_parameters()}, {k: b.detach().clone() for k, b in m.named_buffers()}
 
@@ -172,18 +202,23 @@ def test_encoder_forward_backward_vs_torch(G, B, seed):
     enc = pol.features_extractor
     for training in (False, True):
         f_ref, g32, b32 = oracle_grads(ref, obs, wsum, training, torch.float32)
-        f64, g64, b64 = oracle_grads(ref, obs, wsum, training, torch.float64)
         pol.train(training)
         for p in enc.parameters():
             p.grad = None
         f = enc(obs_d)
         assert rel_err(f.detach().cpu(), f_ref) < RTOL, f"features training={training}"
-        assert rel_err(f.detach().cpu(), f64) < RTOL, f"features (float64 oracle) training={training}"
+        masks = kernel_relu_masks(enc, B)
         (f * wsum.to(DEV)).sum().backward()
-        scale = float(g32["naive_encoder_grid.3.weight"].abs().max())
+        f64, g64, b64 = oracle_grads(ref, obs, wsum, training, torch.float64, masks=masks)
+        assert rel_err(f.detach().cpu(), f64) < RTOL, f"features (float64 oracle) training={training}"
+        scale = float(g64["naive_encoder_grid.3.weight"].abs().max())
         for k, p in enc.named_parameters():
-            assert grad_close(k, p.grad.cpu(), g32[k], training, scale, want64=g64[k]), \
-                f"grad {k} training={training}: vs f64 {rel_err(p.grad.cpu(), g64[k]):.2e}, vs f32 {rel_err(p.grad.cpu(), g32[k]):.2e}"
+            got, want = p.grad.cpu().double(), g64[k]
+            if training and (k.endswith("naive_encoder_grid.0.bias") or k.endswith("naive_encoder_grid.3.bias")):
+                ok = float((got - want).abs().max()) < RTOL * scale          # exactly-zero gradient: rounding noise on both sides
+            else:
+                ok = rel_err(got, want) < RTOL
+            assert ok, f"grad {k} training={training}: vs f64 (kernel tie decisions) {rel_err(got, want):.2e}, vs f32 {rel_err(got, g32[k]):.2e}"
         if training:
             for k, b in enc.named_buffers():
                 assert rel_err(b.cpu().double(), b32[k].double()) < RTOL, k
