@@ -39,8 +39,7 @@ class TensorRolloutBuffer_Grid_Obs:
         self.obs_shape = tuple(observation_space.shape)
         self.actions_shape = int(action_space.shape[0])
         self.device = torch.device(device)
-        if self.device.type != "cuda":
-            raise RuntimeError("TensorRolloutBuffer_Grid_Obs needs a CUDA device (no CPU fallback)")
+        # storage may live on any device (construction-only wiring tests); GAE and the minibatch kernels refuse non-CUDA tensors
         self.gae_lambda, self.gamma = gae_lambda, gamma
         T, N, dev = self.buffer_size, self.n_envs, self.device
         self.observations = torch.zeros(T, N, *self.obs_shape, device=dev)

@@ -16,6 +16,7 @@
 #include "gemm.cuh"
 #include "conv2_tc.cuh"
 #include "conv2_mma.cuh"
+#include "conv2_ts.cuh"
 #include "mma.cuh"
 #include "tma.cuh"
 #include "encoder.cuh"
@@ -1483,6 +1484,7 @@ EncDims make_dims(int B, int G, int state_dim) {
     d.nblk2 = (int)ceil_div(d.items2, CONV2_THREADS);
     d.flat2 = (int64_t)C1 * d.P2;
     d.nrec2 = std::max(std::max(d.nblk2, conv2_mma_chunks(d.G2)), conv2_tc_supported(d.G1, d.G2) ? conv2_tc_tiles(1, d.G2) : 0);
+    if (conv2_ts_supported(d.G1, d.G2)) d.nrec2 = std::max(d.nrec2, conv2_ts_tiles(1, d.G2));
     return d;
 }
 
@@ -1658,7 +1660,11 @@ int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, i
     const int tc_mode = conv2_tc_mode();
     const bool use_tc = tc_mode == 1;
     int nrec2;
-    if (tc_mode & 2) {
+    if ((tc_mode & 32) && conv2_ts_supported(d.G1, d.G2)) {
+        rc = launch_conv2_fwd_ts(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2, part2, B, d.G1, d.G2, stream);
+        if (rc) return rc;
+        nrec2 = conv2_ts_tiles(B, d.G2);
+    } else if (tc_mode & 2) {
         rc = launch_conv2_fwd_mma(ws + w.y1, ws + w.stat1, p->conv2_w, p->conv2_b, ws + w.y2, part2, B, d.G1, d.G2, stream);
         if (rc) return rc;
         nrec2 = conv2_mma_items(B, d.G2);

@@ -45,21 +45,33 @@ class _RatioHistory:
 
 
 class Env_Train_GenNBV:
+    # What `task_registry.make_env` (legged_gym/utils/task_registry.py:98-104) cannot pass: it calls
+    # `task_class(cfg=, sim_params=, physics_engine=, sim_device=, headless=)` only.  A deployment installs the two factories once
+    # (e.g. `Env_Train_GenNBV.sensor_factory = lambda env: IsaacGymSensor(...)`); explicit keyword arguments win.
+    sensor_factory = None          # callable(env) -> SensorSource, called with cfg / num_envs / device already set
+    grid_gt_loader = None          # callable(env) -> [num_scene, G, G, G, 4] tensor (reference: torch.load of the Houses3K GT grid)
+
     def __init__(self, cfg=None, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
                  sensor: SensorSource = None, grid_gt: torch.Tensor = None, num_envs: int = None):
         """cfg: Config_GenNBV_Train-like object; grid_gt: the [num_scene, G, G, G, 4] tensor the reference loads from
-        data_gennbv/train/gt/train_houses3k_grid_gt.pt (env_train_gennbv.py:61-64); sensor: frame source."""
-        if not torch.cuda.is_available():
-            raise RuntimeError("gennbv_b200.Env_Train_GenNBV needs a CUDA device (there is no CPU fallback)")
+        data_gennbv/train/gt/train_houses3k_grid_gt.pt (env_train_gennbv.py:61-64); sensor: frame source.
+        The buffers may be allocated on a non-CUDA device (construction only, e.g. to exercise an entry script's wiring):
+        every kernel call checks its tensors and raises -- there is no CPU compute path."""
         _lib.lib()
         self.cfg = cfg if cfg is not None else Config_GenNBV_Train()
         cfg = self.cfg
+        self.sim_params, self.physics_engine = sim_params, physics_engine
         self.device = torch.device(sim_device)
         self.headless = headless
         self.num_envs = int(num_envs if num_envs is not None else cfg.env.num_envs)
+        if grid_gt is None and type(self).grid_gt_loader is not None:
+            grid_gt = type(self).grid_gt_loader(self)
+        if sensor is None and type(self).sensor_factory is not None:
+            sensor = type(self).sensor_factory(self)
         self.sensor = sensor
         if sensor is None or grid_gt is None:
-            raise ValueError("Env_Train_GenNBV needs a sensor source and the GT grid tensor")
+            raise ValueError("Env_Train_GenNBV needs a sensor source and the GT grid tensor (keyword arguments, or the "
+                             "class-level sensor_factory / grid_gt_loader hooks)")
         N, dev = self.num_envs, self.device
         self.dt = cfg.control.decimation * float(np.float32(cfg.sim.dt))         # drone_robot.py:874-875
         self.max_episode_length = cfg.max_episode_length                          # env_train_base.py:132

@@ -508,7 +508,7 @@ class PPO_Grid_Obs:
         return self.policy.predict(observation, state, episode_start, deterministic)
 
     def learn(self, total_timesteps, callback=None, log_interval=1, eval_env=None, eval_freq=-1, n_eval_episodes=5,
-              tb_log_name="OnPolicyAlgorithm", eval_log_path=None, reset_num_timesteps=True):
+              tb_log_name="PPO", eval_log_path=None, reset_num_timesteps=True):
         """on_policy_algorithm_grid_obs.py:230-298."""
         iteration = 0
         total_timesteps = self._setup_learn(total_timesteps, reset_num_timesteps)

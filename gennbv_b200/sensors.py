@@ -113,3 +113,70 @@ class FrameListSensor(SensorSource):
                     self.dev[s][k].copy_(v, non_blocking=True)
             f = self.dev[s]
         return SensorFrame(depth=f["depth"], seg=f["seg"], rgba=f.get("rgba"), c2w=f["c2w"])
+
+
+def quat_from_euler_xyz(roll, pitch, yaw):
+    """isaacgym.torch_utils.quat_from_euler_xyz: (x, y, z, w) from extrinsic XYZ Euler angles."""
+    cy, sy = torch.cos(yaw * 0.5), torch.sin(yaw * 0.5)
+    cr, sr = torch.cos(roll * 0.5), torch.sin(roll * 0.5)
+    cp, sp = torch.cos(pitch * 0.5), torch.sin(pitch * 0.5)
+    qw = cy * cr * cp + sy * sr * sp
+    qx = cy * sr * cp - sy * cr * sp
+    qy = cy * cr * sp + sy * sr * cp
+    qz = sy * cr * cp - cy * sr * sp
+    return torch.stack([qx, qy, qz, qw], dim=-1)
+
+
+class IsaacGymSensor(SensorSource):
+    """Adapter for a live Isaac Gym simulation: what the reference env does around its camera tensors, behind the
+    `SensorSource` interface.
+
+    `render(poses)` = `set_state(poses)` (env_train_base.py:686-714: root position = pose xyz + env origin, orientation from
+    roll / pitch / yaw), `gym.simulate` + `fetch_results` (env_train_gennbv.py:257-261), then `step_graphics`,
+    `render_all_camera_sensors`, `start_access_image_tensors` ... `end_access_image_tensors` (:349-354) around ONE stacked
+    copy of the per-env wrapped image tensors (:204-227), and `get_camera_view_matrix` for every env (env_train_base.py:777-785,
+    a host array in Isaac's row-vector convention; the env turns it into camera-to-world exactly as the reference does).
+
+    The Isaac Gym modules are injected (`gym`, `gymapi`, `gymtorch`), so that this file imports without Isaac Gym and the
+    adapter can be exercised against a mock (tests/test_isaac_sensor.py); nothing here touches the closed-source API beyond
+    the calls listed above."""
+
+    def __init__(self, gym, sim, envs, camera_handles, root_states, env_origins, height, width, gymapi, gymtorch, skip=1,
+                 contact_forces=None, contact_threshold=1.0):
+        self.gym, self.sim, self.envs, self.camera_handles = gym, sim, list(envs), list(camera_handles)
+        assert len(self.envs) == len(self.camera_handles), "one camera per env (env_train_base.py:781)"
+        self.root_states, self.env_origins, self.skip = root_states, env_origins, skip
+        self.height, self.width, self.gymtorch = height, width, gymtorch
+        self.contact_forces, self.contact_threshold = contact_forces, contact_threshold
+        wrap = lambda kind: [gymtorch.wrap_tensor(gym.get_camera_image_gpu_tensor(sim, e, h, kind))
+                             for e, h in zip(self.envs, self.camera_handles)]
+        self.rgb_cam_tensors = wrap(gymapi.IMAGE_COLOR)               # [H,W,4] u8 each
+        self.depth_cam_tensors = wrap(gymapi.IMAGE_DEPTH)             # [H,W] f32, negative z-depth, -inf = no hit
+        self.seg_cam_tensors = wrap(gymapi.IMAGE_SEGMENTATION)        # [H,W] i32
+
+    def set_state(self, poses):
+        self.root_states[::self.skip, 0:3] = poses[..., 0:3] + self.env_origins.to(poses.device)
+        self.root_states[::self.skip, 3:7] = quat_from_euler_xyz(poses[..., 3], poses[..., 4], poses[..., 5])
+        self.gym.set_actor_root_state_tensor(self.sim, self.gymtorch.unwrap_tensor(self.root_states))
+
+    def get_camera_view_matrix(self):
+        return np.array([self.gym.get_camera_view_matrix(self.sim, e, h) for e, h in zip(self.envs, self.camera_handles)],
+                        dtype=np.float32)
+
+    def render(self, poses):
+        gym, sim = self.gym, self.sim
+        self.set_state(poses)
+        gym.simulate(sim)
+        gym.fetch_results(sim, True)
+        gym.step_graphics(sim)
+        gym.render_all_camera_sensors(sim)
+        gym.start_access_image_tensors(sim)
+        depth = torch.stack(self.depth_cam_tensors).float().contiguous()
+        seg = torch.stack(self.seg_cam_tensors).to(torch.int32).contiguous()
+        rgba = torch.stack(self.rgb_cam_tensors).to(torch.uint8).contiguous()
+        gym.end_access_image_tensors(sim)
+        contact = None
+        if self.contact_forces is not None:                           # drone_robot.py check_termination: |F| > 1 on any body
+            f = self.contact_forces
+            contact = (torch.norm(f.view(len(self.envs), -1, 3), dim=-1) > self.contact_threshold).any(dim=1).to(torch.uint8)
+        return SensorFrame(depth=depth, seg=seg, rgba=rgba, view_matrix=self.get_camera_view_matrix(), contact=contact)

@@ -29,7 +29,7 @@ _MOCKED = [
     "matplotlib", "matplotlib.pyplot", "matplotlib.figure",
     "pytorch3d", "pytorch3d.loss",
     "rsl_rl", "rsl_rl.env", "rsl_rl.runners",
-    "wandb",
+    "wandb", "wandb.sdk", "wandb.sdk.lib", "wandb.sdk.lib.telemetry",
 ]
 
 
