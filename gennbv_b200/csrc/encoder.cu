@@ -1803,7 +1803,11 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
                                                                 gr->conv2_b);
     stage_mark(GNBV_ST_BWD_CONV2_DGRAD, stream);
     int nrec_dg;
-    if (conv2_tc_mode() & 4) {
+    if ((conv2_tc_mode() & 64) && conv2_ts_supported(d.G1, d.G2)) {
+        rc = launch_conv2_dgrad_ts(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1, ws + w.bpart1, B, d.G1, d.G2, stream);
+        if (rc) return rc;
+        nrec_dg = conv2_dgrad_ts_records(B, d.G1);
+    } else if (conv2_tc_mode() & 4) {
         rc = launch_conv2_dgrad_mma(ws + w.dy2cl, p->conv2_w, ws + w.y1, ws + w.stat1, ws + w.g1, ws + w.bpart1, B, d.G1, d.G2, stream);
         if (rc) return rc;
         nrec_dg = B * conv2_dgrad_mma_items_per_sample(d.G1);

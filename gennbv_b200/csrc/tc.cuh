@@ -34,21 +34,35 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
+// One lane of a converged warp (elect.sync).  Together with a PROVABLY warp-uniform role branch (warp index taken through
+// __shfl_sync) this lets ptxas keep the tcgen05.mma operands in uniform registers; under a plain `if (lane == 0)` every MMA is
+// wrapped in a divergence "waterfall" (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~12 instructions and several R2UR latencies each).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
+__device__ __forceinline__ int uniform_warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // ---- mbarrier ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-// Bounded wait (a stuck barrier must never hang the GPU): returns false after ~2^26 polls.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+// Bounded wait (a stuck barrier must never hang the GPU): returns false after ~2^24 polls.
+// A failed poll backs off with nanosleep: a spinning warp otherwise takes its full share of the scheduler's issue slots away
+// from the warps doing the work it waits for (measured: 17 warps with ~12 of them spinning ran the working warps 4x slower).
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, uint32_t sleep_ns = 32) {
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok)
                      : "r"(bar), "r"(parity)
                      : "memory");
         if (ok) return true;
+        if (sleep_ns) asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
     }
     return false;
 }
