@@ -76,6 +76,7 @@ SIGNATURES = {
     "gnbv_encoder_backward": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                       c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_void_p]),
     "gnbv_encoder_workspace_view": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "gnbv_debug_ts_profile": (c_int, [ctypes.POINTER(c_uint64)]),
     "gnbv_encoder_backward_phase": (c_int, [ctypes.POINTER(EncoderParams), c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int,
                                             c_void_p, c_void_p, ctypes.POINTER(EncoderGrads), c_void_p, c_size_t, c_int, c_void_p]),
     "gnbv_ppo_minibatch_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
@@ -109,6 +110,10 @@ SIGNATURES = {
     "gnbv_nn_sqdist_brute": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnbv_scan_points": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int64, c_uint32, c_void_p]),
     "gnbv_keys_to_points": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "gnbv_points_to_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "gnbv_pack_env_keys": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "gnbv_sort_unique_workspace_bytes": (c_size_t, [c_int64]),
+    "gnbv_sort_unique_u64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnbv_gae": (c_int, [c_void_p] * 5 + [c_double, c_double, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

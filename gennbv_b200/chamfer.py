@@ -107,5 +107,6 @@ def accuracy_from_history(pts_history, pc_gt):
     """env_eval_gennbv.py:253-261 for one env: 1 cm voxel dedup of the scanned points, then chamfer to the GT cloud.
     Note the reference writes `(chamfer_distance(...) * 100)[0]`: the tuple is repeated 100 times and `[0]` is the
     unscaled loss -- reproduced."""
-    pc = torch.unique(torch.round(pts_history, decimals=2), dim=0)
+    from . import ops
+    pc = ops.keys_to_points(ops.sort_unique(ops.points_to_keys(pts_history.contiguous()), key_bits=54))      # 1 cm lattice dedup
     return chamfer_distance(pc.unsqueeze(0), pc_gt.unsqueeze(0))[0].unsqueeze(0)

@@ -17,8 +17,12 @@ void set_error(const char* fmt, ...) {
 // ---- kernel-variant switches.  Every variant is parity-tested (tests/test_policy_gpu.py re-runs the encoder parity tests
 // under each setting); the defaults are the fastest measured on B200 at B = 256, 64^3 (profiles/).
 //   GNBV_CONV2_TC  (bit mask) 2 = mma.sync forward, 4 = mma.sync data gradient, 8 = mma.sync weight gradient (register
-//                  path), 16 = TMA-staged weight gradient (overrides 8); 1 = tcgen05 forward
-//                  (conv2_tc.cu; slower, staging-bound); 0 = fp32 CUDA-core kernels.
+//                  path), 16 = TMA-staged weight gradient (overrides 8); 32 = tcgen05 TS-form forward and 64 = tcgen05 TS-form
+//                  data gradient (conv2_ts.cu: A operand in tensor memory, TMA bulk staging, warp-specialised; parity-green,
+//                  measured 0.31 / 0.66 ms against 0.27 / 0.44 ms for the mma.sync kernels at B = 256 -- with N = 16 output
+//                  channels a tcgen05.mma is bound by its A-operand fetch (16 cycles per M128 x N16 x K8 instruction,
+//                  scripts/micro/mma_rate.cu) and the staging traffic saturates shared memory);
+//                  1 = tcgen05 SS-form forward (conv2_tc.cu; slower still); 0 = fp32 CUDA-core kernels.
 //   GNBV_CONV1_MMA (bit mask) 1 = conv1 forward on the tensor cores, 2 = conv1 weight gradient; 0 = CUDA-core TMA kernels.
 //   GNBV_GEMM_MMA  1 = mma.sync 3xTF32 GEMM for the Linear layers, 0 = fp32 CUDA-core GEMM.
 namespace gnbv {

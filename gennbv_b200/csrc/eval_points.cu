@@ -118,9 +118,42 @@ __global__ void keys_to_points_kernel(const int64_t* __restrict__ keys, int64_t 
     pts[3 * i + 2] = __fdiv_rn((float)kz, 100.0f);
 }
 
+// arbitrary world points -> packed 1 cm lattice keys (the same rounding as the history kernel)
+__global__ void points_to_keys_kernel(const float* __restrict__ pts, int64_t n, int64_t* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = pack_key(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+}
+
+// histories of a list of envs -> one array, env r's valid prefix at out[offsets[r] ..), tagged with r in the bits above the key
+__global__ void pack_env_keys_kernel(const int64_t* __restrict__ keys, int64_t cap, const int64_t* __restrict__ env_rows,
+                                     const int64_t* __restrict__ offsets, int tag_shift, int64_t* __restrict__ out) {
+    const int r = blockIdx.y;
+    const int64_t n = offsets[r + 1] - offsets[r];
+    const int64_t* src = keys + env_rows[r] * cap;
+    int64_t* dst = out + offsets[r];
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        dst[j] = src[j] | ((int64_t)r << tag_shift);
+}
+
 }  // namespace gnbv
 
 using namespace gnbv;
+
+extern "C" int gnbv_points_to_keys(const float* points, int64_t num_points, int64_t* keys, void* stream) {
+    GNBV_REQUIRE(points && keys && num_points > 0, "gnbv_points_to_keys: bad arguments");
+    points_to_keys_kernel<<<(unsigned)ceil_div(num_points, 256), 256, 0, (cudaStream_t)stream>>>(points, num_points, keys);
+    GNBV_LAUNCH_CHECK("points_to_keys_kernel");
+    return GNBV_OK;
+}
+
+extern "C" int gnbv_pack_env_keys(const int64_t* keys, int64_t capacity, const int64_t* env_rows, const int64_t* offsets,
+                                  int num_rows, int tag_shift, int64_t* out, void* stream) {
+    GNBV_REQUIRE(keys && env_rows && offsets && out && num_rows > 0 && capacity > 0 && tag_shift >= 54 && tag_shift < 63,
+                 "gnbv_pack_env_keys: bad arguments");
+    pack_env_keys_kernel<<<dim3(64, num_rows), 256, 0, (cudaStream_t)stream>>>(keys, capacity, env_rows, offsets, tag_shift, out);
+    GNBV_LAUNCH_CHECK("pack_env_keys_kernel");
+    return GNBV_OK;
+}
 
 extern "C" int gnbv_scan_points(const float* depth, const int32_t* seg, const float* kinv, const float* c2w, int64_t* keys,
                                 int32_t* counts, int32_t* overflow, int num_envs, int height, int width, int64_t capacity,

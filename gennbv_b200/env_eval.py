@@ -105,15 +105,16 @@ class Env_Eval_GenNBV(Env_Train_GenNBV):
         """`torch.unique(torch.round(pts_target_list[env_idx], decimals=2), dim=0)` (:254-257): the distinct 1 cm lattice
         points scanned so far, in the reference's (lexicographic) row order."""
         c = int(self._pts_count[env_idx])
-        return self._decode(torch.unique(self._pts_keys[env_idx, :c]))
+        return self._decode(ops.sort_unique(self._pts_keys[env_idx, :c].clone(), key_bits=self.ENV_KEY_SHIFT))
 
     ENV_KEY_SHIFT = 54                      # history keys use 54 bits (eval_points.cu); bits 54..62 carry an env rank
     ENVS_PER_SORT = 512
 
     def dedup_clouds(self, env_ids):
         """`torch.unique(torch.round(pts_target_list[e], decimals=2), dim=0)` (:254-257) for many envs at once: the valid key
-        prefixes are tagged with the env's rank in the spare high bits and deduplicated by ONE sort (torch.unique on int64:
-        plumbing), then decoded by one kernel launch.  Returns (points [sum n, 3] f32 packed in env order, sizes list)."""
+        prefixes are gathered into one array, tagged with the env's rank in the spare high bits (gnbv_pack_env_keys),
+        de-duplicated by ONE in-tree radix sort + compaction (gnbv_sort_unique_u64) and decoded by one kernel launch.
+        Returns (points [sum n, 3] f32 packed in env order, sizes list)."""
         dev = self.device
         pts_parts, sizes = [], []
         for c0 in range(0, len(env_ids), self.ENVS_PER_SORT):
@@ -124,10 +125,14 @@ class Env_Eval_GenNBV(Env_Train_GenNBV):
             if maxc == 0:
                 sizes += [0] * len(ids)
                 continue
-            keys = self._pts_keys[:, :maxc] if ids == list(range(self.num_envs)) else self._pts_keys[rows, :maxc]
-            rank = torch.arange(len(ids), device=dev, dtype=torch.int64)
-            valid = torch.arange(maxc, device=dev)[None, :] < cnt[:, None]
-            uniq = torch.unique((keys + (rank << self.ENV_KEY_SHIFT)[:, None])[valid])          # sorted: env rank major, key minor
+            offs = torch.zeros(len(ids) + 1, dtype=torch.int64, device=dev)
+            offs[1:] = torch.cumsum(cnt, 0)
+            total = int(offs[-1])
+            packed = torch.empty(total, dtype=torch.int64, device=dev)
+            _lib.check(_lib.lib().gnbv_pack_env_keys(self._pts_keys.data_ptr(), self._pts_keys.shape[1], rows.data_ptr(), offs.data_ptr(),
+                                                     len(ids), self.ENV_KEY_SHIFT, packed.data_ptr(), ops._stream()), "gnbv_pack_env_keys")
+            nbits = self.ENV_KEY_SHIFT + max(1, (len(ids) - 1).bit_length())
+            uniq = ops.sort_unique(packed, key_bits=nbits)                                       # sorted: env rank major, key minor
             bounds = torch.searchsorted(uniq, torch.arange(len(ids) + 1, device=dev, dtype=torch.int64) << self.ENV_KEY_SHIFT)
             sizes += (bounds[1:] - bounds[:-1]).tolist()
             pts_parts.append(self._decode(uniq))

@@ -159,3 +159,38 @@ def tc_gemm(A, a_strides, B, b_strides, C, M, N, K, bias=None, relu=False, ldc=N
                         _ptr(bias, torch.float32, "bias"), int(relu), workspace.data_ptr(), workspace.numel() * 4, _stream())
     _lib.check(rc, "gnbv_tc_gemm")
     return workspace
+
+
+def sort_unique(keys, key_bits=64):
+    """gnbv_sort_unique_u64: the distinct values of an int64 CUDA tensor in ascending order (in-tree radix sort + compaction;
+    what `torch.unique` did on the eval path).  `keys` must be non-negative below 2**key_bits; it is used as scratch."""
+    n = keys.numel()
+    if n == 0:
+        return keys.new_empty(0)
+    L = _lib.lib()
+    nbytes = L.gnbv_sort_unique_workspace_bytes(n)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+    out = torch.empty(n, dtype=torch.int64, device=keys.device)
+    count = torch.zeros(1, dtype=torch.int64, device=keys.device)
+    rc = L.gnbv_sort_unique_u64(_ptr(keys, torch.int64, "keys"), n, int(key_bits), out.data_ptr(), count.data_ptr(), ws.data_ptr(),
+                                nbytes, _stream())
+    _lib.check(rc, "gnbv_sort_unique_u64")
+    return out[:int(count)]
+
+
+def points_to_keys(points):
+    """gnbv_points_to_keys: [n,3] f32 -> packed 1 cm lattice keys (ascending key order == lexicographic row order)."""
+    n = points.shape[0]
+    keys = torch.empty(n, dtype=torch.int64, device=points.device)
+    if n:
+        _lib.check(_lib.lib().gnbv_points_to_keys(_ptr(points, torch.float32, "points", (n, 3)), n, keys.data_ptr(), _stream()),
+                   "gnbv_points_to_keys")
+    return keys
+
+
+def keys_to_points(keys):
+    pts = torch.empty(keys.shape[0], 3, device=keys.device)
+    if keys.shape[0]:
+        _lib.check(_lib.lib().gnbv_keys_to_points(_ptr(keys, torch.int64, "keys"), keys.shape[0], pts.data_ptr(), _stream()),
+                   "gnbv_keys_to_points")
+    return pts

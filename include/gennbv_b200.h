@@ -227,6 +227,10 @@ int gnbv_encoder_forward(const gnbv_encoder_params* params, const float* obs, in
 #define GNBV_WS_ACT2 4
 int gnbv_encoder_workspace_view(int batch, int grid_size, int state_dim, int which, int64_t* offset_floats, int64_t* count);
 
+/* Profiling aid of the tcgen05 TS-form conv2 forward kernel (csrc/conv2_ts.cu): with GNBV_TS_DEBUG bit 32 set, CTA 0 accumulates the
+ * cycles each warp role spends waiting / working; this copies the 32 counters to the host (synchronises). */
+int gnbv_debug_ts_profile(unsigned long long* out32);
+
 /* Gradient destinations, one per trainable tensor of gnbv_encoder_params (same shapes). */
 typedef struct gnbv_encoder_grads {
     float *conv1_w, *conv1_b, *bn1_w, *bn1_b, *conv2_w, *conv2_b, *bn2_w, *bn2_b;
@@ -400,6 +404,19 @@ int gnbv_scan_points(const float* depth, const int32_t* seg, const float* kinv, 
                      int32_t* counts, int32_t* overflow, int num_envs, int height, int width, int64_t capacity,
                      uint32_t flags, void* stream);
 int gnbv_keys_to_points(const int64_t* keys, int64_t num_keys, float* points, void* stream);
+/* Inverse direction for callers that hold float points (`torch.round(pts, decimals=2)`, env_eval_gennbv.py:254): packed keys. */
+int gnbv_points_to_keys(const float* points, int64_t num_points, int64_t* keys, void* stream);
+/* Histories [num_envs, capacity] of the listed envs -> one array: env_rows[r]'s first offsets[r+1]-offsets[r] keys at
+ * out + offsets[r], each OR-ed with r << tag_shift (tag_shift >= 54), so that ONE sort de-duplicates every env. */
+int gnbv_pack_env_keys(const int64_t* keys, int64_t capacity, const int64_t* env_rows, const int64_t* offsets, int num_rows,
+                       int tag_shift, int64_t* out, void* stream);
+
+/* `torch.unique` on 64-bit keys (env_eval_gennbv.py:254-257 after the key packing), in-tree: stable LSD radix sort over the
+ * low `key_bits` bits (8 bits per pass) followed by a compaction of the run heads.  `keys` [n] is used as a sort buffer
+ * (destroyed); unique_out [>= n] receives the distinct keys in ascending order, *count_out (device) their number. */
+size_t gnbv_sort_unique_workspace_bytes(int64_t n);
+int gnbv_sort_unique_u64(uint64_t* keys, int64_t n, int key_bits, uint64_t* unique_out, int64_t* count_out, void* workspace,
+                         size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

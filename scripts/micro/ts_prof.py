@@ -13,9 +13,8 @@ enc = pol.features_extractor
 for _ in range(3):
     with torch.no_grad(): enc(obs)
 torch.cuda.synchronize()
-h = ctypes.CDLL(_lib.LIB_PATH)
-buf = (ctypes.c_ulonglong * 32)()
-h.gnbv_debug_ts_profile(buf)
+buf = (ctypes.c_uint64 * 32)()
+_lib.check(_lib.lib().gnbv_debug_ts_profile(buf), "gnbv_debug_ts_profile")
 v = list(buf)
 names = {0: "loader.wait_pfree", 1: "loader.wait_raw", 2: "loader.permute", 4: "prod.wait_pfull", 5: "prod.wait_free", 6: "prod.work",
          8: "mma.wait_accfree", 9: "mma.wait_full", 10: "mma.issue", 12: "epi.wait_accfull", 13: "epi.work", 14: "epi.total", 15: "tiles"}

@@ -295,33 +295,6 @@ def test_clip_and_adam_match_torch():
         assert float((p.cpu() - p_ref.detach()).abs().max()) <= 1e-6
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
-def test_tcgen05_conv2_path_is_parity_green(mode):
-    """The tensor-core conv2 forward paths (GNBV_CONV2_TC=1: tcgen05, =2: mma.sync; both 3xTF32 implicit GEMMs) reproduce
-    the fp32 reference in eval and in training mode (batch statistics come from the kernel's own records)."""
-    import subprocess, sys, os
-    code = (
-        "import sys, os; sys.path[:0] = [%r, %r, %r]\n"
-        "import torch, encoder_ref\n"
-        "from test_policy_gpu import make_policy, rel_err\n"
-        "for G, B in ((64, 3), (20, 9), (20, 1)):\n"
-        "    pol, ref, D = make_policy(G, 1)\n"
-        "    g = torch.Generator().manual_seed(0)\n"
-        "    obs = torch.zeros(B, D); obs[:, :600] = torch.randn(B, 600, generator=g)\n"
-        "    obs[:, 600:600 + G ** 3] = torch.randint(-1, 2, (B, G ** 3), generator=g).float()\n"
-        "    for tr in (False, True):\n"
-        "        ref.train(tr); pol.train(tr)\n"
-        "        with torch.no_grad():\n"
-        "            e = rel_err(pol.features_extractor(obs.cuda()).cpu(), ref.features_extractor(obs))\n"
-        "        assert e < 1e-4, (G, tr, e)\n"
-        "print('tc-conv2 ok')\n" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                                     os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"),
-                                     os.path.dirname(os.path.abspath(__file__))))
-    out = subprocess.run([sys.executable, "-c", code], env={**os.environ, "GNBV_CONV2_TC": mode, "GNBV_GEMM_MMA": "0"},
-                         capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "tc-conv2 ok" in out.stdout, out.stdout + out.stderr
-
-
 def test_encoder_forward_with_a_non_ternary_grid():
     """The env only ever produces tri-class grids, but Hybrid_Encoder.forward takes any float observation: the tensor-core
     conv1 kernel must notice inputs that are not exact in TF32 and take its split-operand path."""
@@ -337,25 +310,19 @@ def test_encoder_forward_with_a_non_ternary_grid():
             assert rel_err(pol.features_extractor(obs.to(DEV)).cpu(), ref.features_extractor(obs)) < RTOL
 
 
-_FP32_GEMM = {"GNBV_GEMM_MMA": "0"}
-
-
-@pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "0", **_FP32_GEMM}, {"GNBV_CONV2_TC": "2", **_FP32_GEMM},
-                                 {"GNBV_CONV2_TC": "6", **_FP32_GEMM}, {"GNBV_CONV2_TC": "14", **_FP32_GEMM},
-                                 {"GNBV_CONV1_MMA": "0", **_FP32_GEMM}, {"GNBV_CONV1_MMA": "1", **_FP32_GEMM}, _FP32_GEMM],
+# Kernel variants (csrc/api.cu).  The defaults -- GNBV_CONV2_TC=30 (mma.sync conv2 forward + data gradient, TMA-staged weight
+# gradient), GNBV_CONV1_MMA=3, GNBV_GEMM_MMA=1 -- are exercised by every other test in this file.  Re-run in a subprocess:
+#   * the tcgen05 kernels: TS-form conv2 forward + data gradient (A operand in tensor memory, 32 | 64) and the older SS-form
+#     forward (1), each next to the default kernels for everything else;
+#   * the fp32 CUDA-core baseline of every contraction (all three switches 0).
+@pytest.mark.parametrize("env", [{"GNBV_CONV2_TC": "126"}, {"GNBV_CONV2_TC": "1"},
+                                 {"GNBV_CONV2_TC": "0", "GNBV_CONV1_MMA": "0", "GNBV_GEMM_MMA": "0"}],
                          ids=lambda e: ",".join(f"{k[5:]}={v}" for k, v in e.items()))
-def test_every_conv_kernel_variant_passes_the_encoder_parity_tests(env):
-    """Defaults (csrc/api.cu): GNBV_CONV2_TC=30 (mma.sync conv2 forward + data gradient + TMA-staged weight gradient),
-    GNBV_CONV1_MMA=3, GNBV_GEMM_MMA=1 -- exercised by every other test in this file.  Here the GEMM test, the encoder
-    forward/backward parity tests against torch autograd (all grid sizes, eval and training BN), the non-ternary-grid test and
-    the golden policy test are re-run in a subprocess with the other settings -- CUDA-core conv2 kernels (0), partial mixes
-    (2, 6), the register-path weight gradient (14), conv1 on CUDA cores (0) / forward only on
-    tensor cores (1), the fp32 CUDA-core GEMM (0) -- so that every kernel variant stays parity-green.  (The convolution
-    variants are run next to the fp32 GEMM: exactly the combinations measured during round 1.)"""
+def test_kernel_variants_pass_the_encoder_parity_tests(env):
     import subprocess, sys
     here = os.path.abspath(__file__)
     out = subprocess.run([sys.executable, "-m", "pytest", here, "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider", "-k",
                           "encoder_forward_backward_vs_torch or policy_matches_reference_golden_g20 or non_ternary or sgemm_modes"],
-                         env={**os.environ, **env}, capture_output=True, text=True, timeout=900,
+                         env={**os.environ, **env}, capture_output=True, text=True, timeout=1200,
                          cwd=os.path.dirname(os.path.dirname(here)))
     assert out.returncode == 0 and " passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
