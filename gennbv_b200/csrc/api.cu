@@ -24,7 +24,8 @@ void set_error(const char* fmt, ...) {
 //                  scripts/micro/mma_rate.cu) and the staging traffic saturates shared memory);
 //                  1 = tcgen05 SS-form forward (conv2_tc.cu; slower still); 0 = fp32 CUDA-core kernels.
 //   GNBV_CONV1_MMA (bit mask) 1 = conv1 forward on the tensor cores, 2 = conv1 weight gradient; 0 = CUDA-core TMA kernels.
-//   GNBV_GEMM_MMA  1 = mma.sync 3xTF32 GEMM for the Linear layers, 0 = fp32 CUDA-core GEMM.
+//   GNBV_GEMM_MMA  (bit mask) 1 = mma.sync 3xTF32 GEMM for the Linear layers (0 = fp32 CUDA-core GEMM), 2 = the large GEMMs
+//                  (grid Linear forward / dX / dW) on the tcgen05 warp-specialised pipeline of tc_gemm.cu.  Default 3.
 namespace gnbv {
 static int env_mode(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -32,7 +33,7 @@ static int env_mode(const char* name, int dflt) {
 }
 int conv2_tc_mode() { static const int m = env_mode("GNBV_CONV2_TC", 30); return m; }
 int conv1_mma_mode() { static const int m = env_mode("GNBV_CONV1_MMA", 3); return m; }
-int gemm_mma_mode() { static const int m = env_mode("GNBV_GEMM_MMA", 1); return m; }
+int gemm_mma_mode() { static const int m = env_mode("GNBV_GEMM_MMA", 3); return m; }
 }  // namespace gnbv
 
 namespace gnbv {

@@ -305,9 +305,17 @@ int gemm_splits(int M, int N, int K) {
     return s;
 }
 
+// The large contractions (the grid Linear layer: 7 GFLOP forward at B = 256, twice that backward) go to the tcgen05 pipeline
+// of tc_gemm.cu when GNBV_GEMM_MMA has bit 2 set (default): measured 0.082 / 0.077 / 0.078 ms against 0.154 / 0.152 / 0.148 ms
+// for the mma.sync kernel (forward / dX / dW at B = 256).  Small GEMMs stay on mma.sync (launch + TMEM set-up dominate there).
+static bool use_tcgen05(int M, int N, int K) {
+    return (gemm_mma_mode() & 2) && N >= 256 && 2.0 * M * N * K >= 1.0e9;
+}
+
 size_t gemm_workspace_floats(int M, int N, int K) {
     int s = gemm_splits(M, N, K);
-    return s > 1 ? (size_t)s * M * N : 0;
+    const size_t a = s > 1 ? (size_t)s * M * N : 0;
+    return use_tcgen05(M, N, K) ? std::max(a, tc_gemm_workspace_floats(M, N, K)) : a;
 }
 
 int launch_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int64_t sb_k, int64_t sb_n, float* C,
@@ -315,6 +323,7 @@ int launch_gemm(const float* A, int64_t sa_m, int64_t sa_k, const float* B, int6
     GNBV_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "gemm: bad arguments (M=%d N=%d K=%d)", M, N, K);
     GNBV_REQUIRE(sa_k == 1 || sa_m == 1, "gemm: A must be contiguous along m or k");
     GNBV_REQUIRE(sb_n == 1 || sb_k == 1, "gemm: B must be contiguous along n or k");
+    if (workspace && use_tcgen05(M, N, K)) return launch_tc_gemm(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, ep, workspace, stream);
     GemmArgs g;
     g.A = A; g.sa_m = sa_m; g.sa_k = sa_k; g.B = B; g.sb_k = sb_k; g.sb_n = sb_n; g.C = C; g.ldc = ldc;
     g.M = M; g.N = N; g.K = K; g.bias = ep.bias; g.relu = ep.relu;
