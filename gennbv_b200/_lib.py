@@ -59,6 +59,7 @@ SIGNATURES = {
                                                       c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
     "gnbv_scan_raycast": (c_int, [c_void_p] * 9 + [c_size_t, c_int, c_int, c_int, c_int, c_uint32, c_void_p]),
     "gnbv_grid_update": (c_int, [c_void_p] * 4 + [c_int64, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    "gnbv_grid_update_sparse": (c_int, [c_void_p] * 4 + [c_int64, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "gnbv_voxelize_masks": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p),
                                     ctypes.POINTER(c_int64)]),
     "gnbv_points_to_voxel_mask": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

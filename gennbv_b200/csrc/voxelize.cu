@@ -363,6 +363,92 @@ grid_update_kernel(const uint32_t* __restrict__ tmask, const uint32_t* __restric
     }
 }
 
+// The same update moving only the bytes that can change.  A 16-byte group (4 voxels) no ray touched this step keeps its
+// prob / scanned values, so for it the kernel reads prob (to form the tri-class value, which must be written to this step's
+// observation row regardless) and writes tri: 8 B per voxel instead of 24.  Touched groups take the full path.  The coverage
+// sum is kept INCREMENTALLY: scanned_gt only changes at target voxels, so partial = sum over touched groups of
+// (scanned_new - scanned_old) -- exact small integers in fp32 -- and cov_sum[n] += the env's partials (coverage_add_kernel).
+__global__ void __launch_bounds__(K2_THREADS)
+grid_update_sparse_kernel(const uint32_t* __restrict__ tmask, const uint32_t* __restrict__ rmask,
+                          const float* __restrict__ grid_gt, float* __restrict__ prob, float* __restrict__ scan,
+                          float* __restrict__ tri, int64_t tri_stride, float* __restrict__ partial,
+                          int V, int words, int chunks) {
+    const int n = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+    const size_t base = (size_t)n * V;
+    const uint32_t* tm = tmask + (size_t)n * words;
+    const uint32_t* rm = rmask + (size_t)n * words;
+    float* trin = tri + (size_t)n * tri_stride;
+    float dcov = 0.0f;
+    const int v0 = chunk * K2_CHUNK;
+    float4 p[K2_UNROLL], s[K2_UNROLL], g[K2_UNROLL];
+    uint32_t tb[K2_UNROLL], rb[K2_UNROLL];
+    bool ok[K2_UNROLL];
+#pragma unroll
+    for (int k = 0; k < K2_UNROLL; ++k) {
+        const int v = v0 + (k * K2_THREADS + tid) * 4;
+        ok[k] = v < V;
+        tb[k] = rb[k] = 0;
+        if (ok[k]) {                                        // mask words and prob of all groups first: nothing here depends on a load
+            tb[k] = __ldg(tm + (v >> 5));
+            rb[k] = __ldg(rm + (v >> 5));
+            p[k] = ld_stream4(prob + base + v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K2_UNROLL; ++k) {
+        const int v = v0 + (k * K2_THREADS + tid) * 4;
+        tb[k] = (tb[k] >> (v & 31)) & 15u;
+        rb[k] = (rb[k] >> (v & 31)) & 15u;
+        if (ok[k] && tb[k]) {                               // scanned_gt can only change where a target voxel is
+            s[k] = ld_stream4(scan + base + v);
+            g[k] = ldg_stream4(grid_gt + base + v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K2_UNROLL; ++k) {
+        if (!ok[k]) continue;
+        const int v = v0 + (k * K2_THREADS + tid) * 4;
+        float4 t;
+        if (tb[k]) {
+            float before = (s[k].x + s[k].y) + (s[k].z + s[k].w), after = 0.0f;
+            update4(p[k], s[k], g[k], t, tb[k], rb[k], after);
+            dcov += after - before;
+            stg_stream4(prob + base + v, p[k]);
+            stg_stream4(scan + base + v, s[k]);
+        } else {
+            float* pp = &p[k].x; float* tt = &t.x;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float pr = pp[e];
+                if (rb[k] & (1u << e)) pr = __fsub_rn(pr, 0.05f);
+                pp[e] = pr;
+                tt[e] = (pr > 0.5f ? 1.0f : 0.0f) - (pr < 0.0f ? 1.0f : 0.0f);
+            }
+            if (rb[k]) stg_stream4(prob + base + v, p[k]);
+        }
+        stg_stream4(trin + v, t);
+    }
+    __shared__ float wsum[K2_THREADS / 32];
+    dcov = warp_sum(dcov);
+    if ((tid & 31) == 0) wsum[tid >> 5] = dcov;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < K2_THREADS / 32; ++w) t += wsum[w];
+        partial[(size_t)n * chunks + chunk] = t;
+    }
+}
+
+__global__ void coverage_add_kernel(const float* __restrict__ partial, float* __restrict__ cov_sum, int N, int chunks) {
+    int n = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float t = 0.0f;
+    for (int c = lane; c < chunks; c += 32) t += partial[(size_t)n * chunks + c];
+    t = warp_sum(t);
+    if (lane == 0) cov_sum[n] += t;
+}
+
 __global__ void coverage_finalize_kernel(const float* __restrict__ partial, float* __restrict__ cov_sum, int N, int chunks) {
     int n = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
@@ -497,9 +583,25 @@ extern "C" int gnbv_scan_raycast(const float* depth, const int32_t* seg, const f
     return GNBV_OK;
 }
 
+static int grid_update_impl(const float* grid_gt, float* prob_grid, float* scanned_gt, float* tri_out, int64_t tri_row_stride,
+                            float* cov_sum, void* workspace, size_t workspace_bytes, int N, int G, bool sparse, void* stream_);
+
 extern "C" int gnbv_grid_update(const float* grid_gt, float* prob_grid, float* scanned_gt, float* tri_out,
                                 int64_t tri_row_stride, float* cov_sum, void* workspace, size_t workspace_bytes, int N,
-                                int G, void* stream_) {
+                                int G, void* stream) {
+    return grid_update_impl(grid_gt, prob_grid, scanned_gt, tri_out, tri_row_stride, cov_sum, workspace, workspace_bytes, N, G,
+                            false, stream);
+}
+
+extern "C" int gnbv_grid_update_sparse(const float* grid_gt, float* prob_grid, float* scanned_gt, float* tri_out,
+                                       int64_t tri_row_stride, float* cov_sum, void* workspace, size_t workspace_bytes, int N,
+                                       int G, void* stream) {
+    return grid_update_impl(grid_gt, prob_grid, scanned_gt, tri_out, tri_row_stride, cov_sum, workspace, workspace_bytes, N, G,
+                            true, stream);
+}
+
+static int grid_update_impl(const float* grid_gt, float* prob_grid, float* scanned_gt, float* tri_out, int64_t tri_row_stride,
+                            float* cov_sum, void* workspace, size_t workspace_bytes, int N, int G, bool sparse, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     GNBV_REQUIRE(grid_gt && prob_grid && scanned_gt && tri_out && cov_sum, "gnbv_grid_update: null pointer argument");
     GNBV_REQUIRE(N > 0 && G > 0, "gnbv_grid_update: N, G must be positive");
@@ -514,6 +616,15 @@ extern "C" int gnbv_grid_update(const float* grid_gt, float* prob_grid, float* s
     const bool vec = (V % 4 == 0) && (tri_row_stride % 4 == 0) && (((uintptr_t)grid_gt | (uintptr_t)prob_grid |
                                                                      (uintptr_t)scanned_gt | (uintptr_t)tri_out) & 15) == 0;
     dim3 grid2((unsigned)L.chunks, (unsigned)N);
+    if (sparse && vec) {
+        grid_update_sparse_kernel<<<grid2, K2_THREADS, 0, stream>>>(tmask, rmask, grid_gt, prob_grid, scanned_gt, tri_out,
+                                                                    tri_row_stride, partial, (int)V, (int)L.words, (int)L.chunks);
+        GNBV_LAUNCH_CHECK("grid_update_sparse_kernel");
+        coverage_add_kernel<<<(unsigned)ceil_div(N, 8), 256, 0, stream>>>(partial, cov_sum, N, (int)L.chunks);
+        GNBV_LAUNCH_CHECK("coverage_add_kernel");
+        return GNBV_OK;
+    }
+    GNBV_REQUIRE(!sparse, "gnbv_grid_update_sparse: needs 16-byte aligned grids and G^3, tri_row_stride multiples of 4");
     if (vec)
         grid_update_kernel<true><<<grid2, K2_THREADS, 0, stream>>>(tmask, rmask, grid_gt, prob_grid, scanned_gt, tri_out,
                                                                    tri_row_stride, partial, (int)V, (int)L.words, (int)L.chunks);

@@ -133,6 +133,7 @@ class Env_Train_GenNBV:
         self.obs_flat = self._obs_pp[0]
         self._dones_u8 = self._dones_pp[0]
         self._cov_sum = torch.zeros(N, device=dev)
+        self._sparse_update = (G ** 3) % 4 == 0 and self.obs_dim % 4 == 0 and self._state_dim % 4 == 0
         self._num_targets = torch.zeros(N, dtype=torch.int32, device=dev)
         self._workspace = ops.voxelize_workspace(N, G, dev)
         # ---- rewards (drone_robot.py:660-691: scale *= dt, zero scales dropped)
@@ -237,6 +238,8 @@ class Env_Train_GenNBV:
 
     def _reset_flagged(self, clear):
         L = _lib.lib()
+        if self._sparse_update:
+            self._cov_sum.masked_fill_(self._reset_u8.view(torch.bool), 0.0)       # carried coverage sum of the envs being reset
         _lib.check(L.gnbv_reset_envs(self._reset_u8.data_ptr(), self.prob_grid.data_ptr(), self.scanned_gt_grid.data_ptr(),
                                      self.pose_hist.data_ptr(), self.rgb_hist.data_ptr(), self._ratio.data_ptr(),
                                      self.actions.data_ptr(), self.episode_length_buf.data_ptr(),
@@ -298,8 +301,9 @@ class Env_Train_GenNBV:
                          self._workspace, self._num_targets, raw_depth=True)
         if ev is not None:
             ev[1].record()
+        # sparse update: groups of voxels no ray touched are not rewritten, the coverage sum is carried across steps
         ops.grid_update(self.grid_gt, self.prob_grid, self.scanned_gt_grid, self.obs_flat.view(-1)[self._state_dim:],
-                        self._cov_sum, self._workspace, tri_row_stride=self.obs_dim)
+                        self._cov_sum, self._workspace, tri_row_stride=self.obs_dim, sparse=self._sparse_update)
         if ev is not None:
             ev[2].record()
         self._after_occ_grid_update(frame, c2w)

@@ -82,8 +82,9 @@ def scan_raycast(depth, seg, kinv, c2w, range_gt, voxel_size, pose_xyz, grid_siz
     _lib.check(rc, "gnbv_scan_raycast")
 
 
-def grid_update(grid_gt, prob_grid, scanned_gt, tri_out, cov_sum, workspace, tri_row_stride=None):
-    """gnbv_grid_update: phase 2 of the step (dense prob / tri / scanned_gt / coverage pass)."""
+def grid_update(grid_gt, prob_grid, scanned_gt, tri_out, cov_sum, workspace, tri_row_stride=None, sparse=False):
+    """gnbv_grid_update: phase 2 of the step (dense prob / tri / scanned_gt / coverage pass).  sparse=True:
+    gnbv_grid_update_sparse (untouched 16-byte groups are not rewritten; cov_sum is in/out and incremented)."""
     N, G = grid_gt.shape[0], grid_gt.shape[1]
     V = G ** 3
     if tri_row_stride is None:
@@ -92,7 +93,8 @@ def grid_update(grid_gt, prob_grid, scanned_gt, tri_out, cov_sum, workspace, tri
         tri_ptr = _ptr(tri_out, torch.float32, "tri_out")
         if tri_out.numel() < (N - 1) * tri_row_stride + V:
             raise RuntimeError("tri_out view too small for tri_row_stride")
-    rc = _lib.lib().gnbv_grid_update(
+    fn = _lib.lib().gnbv_grid_update_sparse if sparse else _lib.lib().gnbv_grid_update
+    rc = fn(
         _ptr(grid_gt, torch.float32, "grid_gt", (N, G, G, G)), _ptr(prob_grid, torch.float32, "prob_grid", (N, G, G, G)),
         _ptr(scanned_gt, torch.float32, "scanned_gt", (N, G, G, G)), tri_ptr, tri_row_stride,
         _ptr(cov_sum, torch.float32, "cov_sum", (N,)), _ptr(workspace, torch.uint8, "workspace"), workspace.numel(),

@@ -104,6 +104,13 @@ int gnbv_grid_update(const float* grid_gt, float* prob_grid, float* scanned_gt,
                      float* tri_out, int64_t tri_row_stride, float* cov_sum,
                      void* workspace, size_t workspace_bytes, int num_envs, int grid_size, void* stream);
 
+/* gnbv_grid_update moving only the bytes that can change: 16-byte groups no ray touched keep their prob / scanned values and cost
+ * 8 B per voxel (prob read, tri write) instead of 24.  cov_sum is IN/OUT here: it must hold the env's coverage sum before the
+ * step (0 after a reset) and receives the exact increment.  Needs 16-byte aligned grids, G^3 and tri_row_stride % 4 == 0. */
+int gnbv_grid_update_sparse(const float* grid_gt, float* prob_grid, float* scanned_gt,
+                            float* tri_out, int64_t tri_row_stride, float* cov_sum,
+                            void* workspace, size_t workspace_bytes, int num_envs, int grid_size, void* stream);
+
 /* Debug/compat view of the step's intermediate sets, valid after gnbv_voxelize_step on the same
  * workspace: bit v of row n (v = (x*G+y)*G+z, little-endian within u32 words) of
  *   target mask  = voxels returned by scanned_pts_to_idx_3D (+unique) for env n  (utils.py:230-270)

@@ -192,6 +192,31 @@ def test_full_size_against_the_c_oracle():
     assert int(o["num_targets"].min()) >= 0 and int(o["num_targets"].max()) > 100
 
 
+@pytest.mark.parametrize("N,H,W,G", [(6, 48, 48, 20), (16, 128, 128, 64)])
+def test_sparse_update_equals_dense_update(N, H, W, G):
+    """gnbv_grid_update_sparse (untouched 16-byte groups not rewritten, coverage carried incrementally) leaves prob / scanned /
+    tri and the coverage sums bit-identical to the dense pass, step after step on carried state."""
+    c = synthetic_case(N, H, W, G, 2, 91, steps=4)
+    kinv, rg, vs, gt = (cu(c[k]) for k in ("kinv", "range_gt", "vs", "grid_gt"))
+    ws = ops.voxelize_workspace(N, G, DEV)
+    D = 600 + G ** 3 + 8192
+    state = {}
+    for mode in ("dense", "sparse"):
+        prob = torch.zeros(N, G, G, G, device=DEV); scan = torch.zeros_like(prob)
+        obs = torch.full((N, D), 5.0, device=DEV)
+        cov = torch.zeros(N, device=DEV)
+        hist = []
+        for depth, seg, c2w, xyz in c["frames"]:
+            ops.scan_raycast(cu(depth), cu(seg), kinv, cu(c2w), rg, vs, cu(xyz), G, ws, raw_depth=True)
+            ops.grid_update(gt, prob, scan, obs.view(-1)[600:], cov, ws, tri_row_stride=D, sparse=(mode == "sparse"))
+            hist.append((prob.clone(), scan.clone(), obs.clone(), cov.clone()))
+        state[mode] = hist
+    for t, (a, b) in enumerate(zip(state["dense"], state["sparse"])):
+        for x, y, name in zip(a, b, ("prob", "scanned", "obs/tri", "cov_sum")):
+            assert torch.equal(x, y), f"{name}, step {t}"
+    assert float(state["sparse"][-1][3].min()) > 0
+
+
 def test_reset_grids():
     N, G = 5, 20
     prob = torch.rand(N, G, G, G, device=DEV); scan = torch.rand_like(prob)
