@@ -7,7 +7,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgennbv_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _lib = None
 
@@ -20,14 +20,16 @@ class EncoderParams(ctypes.Structure):
     """gnbv_encoder_params (include/gennbv_b200.h): 24 device pointers in declaration order."""
     FIELDS = ["conv1_w", "conv1_b", "bn1_w", "bn1_b", "bn1_rm", "bn1_rv", "bn1_nbt",
               "conv2_w", "conv2_b", "bn2_w", "bn2_b", "bn2_rm", "bn2_rv", "bn2_nbt",
-              "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b"]
+              "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b",
+              "rgb_conv1_w", "rgb_conv1_b", "rgb_conv2_w", "rgb_conv2_b", "rgb_fc_w", "rgb_fc_b"]     # last six: semantic branch or NULL
     _fields_ = [(f, ctypes.c_void_p) for f in FIELDS]
 
 
 class EncoderGrads(ctypes.Structure):
     """gnbv_encoder_grads: 16 device pointers in declaration order (== Hybrid_Encoder._param_list())."""
     FIELDS = ["conv1_w", "conv1_b", "bn1_w", "bn1_b", "conv2_w", "conv2_b", "bn2_w", "bn2_b",
-              "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b"]
+              "grid_fc_w", "grid_fc_b", "act_fc1_w", "act_fc1_b", "act_fc2_w", "act_fc2_b", "out_fc_w", "out_fc_b",
+              "rgb_conv1_w", "rgb_conv1_b", "rgb_conv2_w", "rgb_conv2_b", "rgb_fc_w", "rgb_fc_b"]
     _fields_ = [(f, ctypes.c_void_p) for f in FIELDS]
 
 

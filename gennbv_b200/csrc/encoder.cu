@@ -20,6 +20,7 @@
 #include "mma.cuh"
 #include "tma.cuh"
 #include "encoder.cuh"
+#include "sem2d.cuh"
 
 #include <stdlib.h>
 
@@ -1491,6 +1492,7 @@ EncDims make_dims(int B, int G, int state_dim) {
 // workspace carve-up (floats). Forward activations that backward needs stay here between the two calls.
 struct EncWs {
     size_t pe, h1, cat, y1, part1, stat1, y2, part2, stat2, act2, gemm, total;
+    size_t s_out1, s_out2, s_feat_pre, s_dflat, s_dy1, s_scratch;       // 2-D semantic branch (used only when its parameters are given)
     // backward-only
     size_t dz, dcat, dh1, dact2, dy2cl, g1, bn2part, coef2, bpart1, coef1, wg2part, wg1part;
     int nblk_dg, nrec_dg, nblk_wg2, nblk_wg1, wg2_pps, wg1_ips;
@@ -1505,7 +1507,7 @@ EncWs make_ws(const EncDims& d, bool backward) {
     const size_t B = d.B;
     w.pe = take(B * 4 * d.S);
     w.h1 = take(B * d.HID);
-    w.cat = take(B * 2 * d.HID);
+    w.cat = take(B * 3 * d.HID);                               // [action | grid | (semantic)] : row stride 2 or 3 x HID at run time
     w.y1 = take(B * (size_t)d.P1 * C1);
     w.part1 = take(B * (size_t)d.nrec1 * PART_STRIDE);
     w.stat1 = take(4 * C1);
@@ -1515,13 +1517,18 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.merge1 = take((size_t)ceil_div(B * (size_t)d.nrec1, MERGE_FAN) * PART_STRIDE);
     w.merge2 = take((size_t)ceil_div(B * (size_t)d.nrec2, MERGE_FAN) * PART_STRIDE);
     w.act2 = take(B * (size_t)d.flat2);
+    w.s_out1 = take(sem2d_out1_floats(d.B));
+    w.s_out2 = take(sem2d_out2_floats(d.B));
     size_t g = 0;
+    g = std::max(g, gemm_workspace_floats(d.B, d.HID, sem2d_flat()));
+    g = std::max(g, gemm_workspace_floats(d.B, d.FEAT, 3 * d.HID));
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, 4 * d.S));
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, d.HID));
     g = std::max(g, gemm_workspace_floats(d.B, d.HID, (int)d.flat2));
     g = std::max(g, gemm_workspace_floats(d.B, d.FEAT, 2 * d.HID));
     w.bmerge1 = 0;
     w.dz = w.dcat = w.dh1 = w.dact2 = w.dy2cl = w.g1 = w.bn2part = w.coef2 = w.bpart1 = w.coef1 = w.wg2part = w.wg1part = 0;
+    w.s_dflat = w.s_dy1 = w.s_scratch = 0;
     w.nblk_dg = (int)ceil_div((int64_t)d.G1 * d.G1 * 2 * ceil_div((d.G1 + 1) / 2, DG2_ZT), DG2_THREADS);
     w.nrec_dg = std::max(w.nblk_dg, conv2_dgrad_mma_items_per_sample(d.G1));     // records per sample of either dgrad kernel
     w.wg2_pps = (int)std::max<int64_t>(1, ceil_div((int64_t)d.B * d.G2 * d.G2, (int64_t)WG2_MAX_BLOCKS));   // rows per block
@@ -1531,7 +1538,14 @@ EncWs make_ws(const EncDims& d, bool backward) {
     w.nblk_wg1 = (int)ceil_div(w.wg1_items, (int64_t)(WG1_THREADS / 4) * w.wg1_ips);
     if (backward) {
         w.dz = take(B * d.FEAT);
-        w.dcat = take(B * 2 * d.HID);
+        w.dcat = take(B * 3 * d.HID);
+        w.s_dflat = take(sem2d_out2_floats(d.B));
+        w.s_dy1 = take(sem2d_out1_floats(d.B));
+        w.s_scratch = take(sem2d_scratch_floats(d.B));
+        g = std::max(g, gemm_workspace_floats(d.B, 3 * d.HID, d.FEAT));
+        g = std::max(g, gemm_workspace_floats(d.FEAT, 3 * d.HID, d.B));
+        g = std::max(g, gemm_workspace_floats(d.B, sem2d_flat(), d.HID));
+        g = std::max(g, gemm_workspace_floats(d.HID, sem2d_flat(), d.B));
         w.dh1 = take(B * d.HID);
         w.dact2 = take(B * (size_t)d.flat2);
         w.dy2cl = take(B * (size_t)d.flat2);
@@ -1602,6 +1616,10 @@ int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, i
     GNBV_REQUIRE(((uintptr_t)workspace & 255) == 0, "gnbv_encoder_forward: workspace must be 256 B aligned");
     float* ws = reinterpret_cast<float*>(workspace);
     const int B = batch;
+    const bool sem = p->rgb_conv1_w != nullptr;               // 2-D semantic branch: third 256-wide block of `cat`
+    GNBV_REQUIRE(!sem || (p->rgb_conv1_b && p->rgb_conv2_w && p->rgb_conv2_b && p->rgb_fc_w && p->rgb_fc_b),
+                 "gnbv_encoder_forward: the semantic branch needs all six rgb_* parameters");
+    const int CAT = (sem ? 3 : 2) * d.HID;
     GemmEpilogue relu_ep;
     relu_ep.relu = 1;
     int rc;
@@ -1613,7 +1631,7 @@ int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, i
     rc = launch_gemm(ws + w.pe, 4 * d.S, 1, p->act_fc1_w, 1, 4 * d.S, ws + w.h1, d.HID, B, d.HID, 4 * d.S, relu_ep, ws + w.gemm, stream);
     if (rc) return rc;
     relu_ep.bias = p->act_fc2_b;
-    rc = launch_gemm(ws + w.h1, d.HID, 1, p->act_fc2_w, 1, d.HID, ws + w.cat, 2 * d.HID, B, d.HID, d.HID, relu_ep, ws + w.gemm, stream);
+    rc = launch_gemm(ws + w.h1, d.HID, 1, p->act_fc2_w, 1, d.HID, ws + w.cat, CAT, B, d.HID, d.HID, relu_ep, ws + w.gemm, stream);
     if (rc) return rc;
     // ---- grid branch
     stage_mark(GNBV_ST_FWD_CONV1, stream);
@@ -1694,13 +1712,24 @@ int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, i
     // Linear(16*G2^3, 256)+ReLU -> cat[:, 256:512]
     stage_mark(GNBV_ST_FWD_GRID_FC, stream);
     relu_ep.bias = p->grid_fc_b;
-    rc = launch_gemm(ws + w.act2, d.flat2, 1, p->grid_fc_w, 1, d.flat2, ws + w.cat + d.HID, 2 * d.HID, B, d.HID, (int)d.flat2,
+    rc = launch_gemm(ws + w.act2, d.flat2, 1, p->grid_fc_w, 1, d.flat2, ws + w.cat + d.HID, CAT, B, d.HID, (int)d.flat2,
                      relu_ep, ws + w.gemm, stream);
     if (rc) return rc;
+    if (sem) {
+        // frames live behind the grid columns of the observation row (env_wrapper_gennbv_train.py:102-110: state | grid | state_rgb)
+        const int64_t rgb_off = (int64_t)state_dim + (int64_t)d.G * d.G * d.G;
+        rc = launch_sem2d_forward(obs, obs_row_stride, row_index, rgb_off, p->rgb_conv1_w, p->rgb_conv1_b, p->rgb_conv2_w,
+                                  p->rgb_conv2_b, ws + w.s_out1, ws + w.s_out2, B, stream);
+        if (rc) return rc;
+        relu_ep.bias = p->rgb_fc_b;
+        rc = launch_gemm(ws + w.s_out2, sem2d_flat(), 1, p->rgb_fc_w, 1, sem2d_flat(), ws + w.cat + 2 * d.HID, CAT, B, d.HID,
+                         sem2d_flat(), relu_ep, ws + w.gemm, stream);
+        if (rc) return rc;
+    }
     // fuse: Linear(512,256)+ReLU -> features
     stage_mark(GNBV_ST_FWD_OUT_FC, stream);
     relu_ep.bias = p->out_fc_b;
-    rc = launch_gemm(ws + w.cat, 2 * d.HID, 1, p->out_fc_w, 1, 2 * d.HID, features, d.FEAT, B, d.FEAT, 2 * d.HID, relu_ep,
+    rc = launch_gemm(ws + w.cat, CAT, 1, p->out_fc_w, 1, CAT, features, d.FEAT, B, d.FEAT, CAT, relu_ep,
                      ws + w.gemm, stream);
     stage_mark(GNBV_ST_FWD_END, stream);
     return rc;
@@ -1738,6 +1767,10 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
                  workspace_bytes, w.total * 4);
     float* ws = reinterpret_cast<float*>(workspace);
     const int B = batch, H = d.HID;
+    const bool sem = p->rgb_conv1_w != nullptr;
+    GNBV_REQUIRE(!sem || (gr->rgb_conv1_w && gr->rgb_conv1_b && gr->rgb_conv2_w && gr->rgb_conv2_b && gr->rgb_fc_w && gr->rgb_fc_b),
+                 "gnbv_encoder_backward: the semantic branch needs all six rgb_* gradient pointers");
+    const int CAT = (sem ? 3 : 2) * H;
     GemmEpilogue none;
     int rc;
     auto blocks = [](int64_t n) { return (unsigned)ceil_div(n, 256); };
@@ -1746,17 +1779,17 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
     // ---- fuse layer: features = relu(cat W^T + b)
     relu_mask_kernel<<<blocks((int64_t)B * d.FEAT), 256, 0, stream>>>(dfeatures, d.FEAT, ws + w.dz, d.FEAT, features, d.FEAT, B, d.FEAT);
     GNBV_LAUNCH_CHECK("relu_mask_kernel");
-    rc = launch_gemm(ws + w.dz, 1, d.FEAT, ws + w.cat, 2 * H, 1, gr->out_fc_w, 2 * H, d.FEAT, 2 * H, B, none, ws + w.gemm, stream);
+    rc = launch_gemm(ws + w.dz, 1, d.FEAT, ws + w.cat, CAT, 1, gr->out_fc_w, CAT, d.FEAT, CAT, B, none, ws + w.gemm, stream);
     if (rc) return rc;
     colsum_kernel<<<blocks(d.FEAT), 256, 0, stream>>>(ws + w.dz, d.FEAT, B, d.FEAT, gr->out_fc_b);
-    rc = launch_gemm(ws + w.dz, d.FEAT, 1, p->out_fc_w, 2 * H, 1, ws + w.dcat, 2 * H, B, 2 * H, d.FEAT, none, ws + w.gemm, stream);
+    rc = launch_gemm(ws + w.dz, d.FEAT, 1, p->out_fc_w, CAT, 1, ws + w.dcat, CAT, B, CAT, d.FEAT, none, ws + w.gemm, stream);
     if (rc) return rc;
-    relu_mask_kernel<<<blocks((int64_t)B * 2 * H), 256, 0, stream>>>(ws + w.dcat, 2 * H, ws + w.dcat, 2 * H, ws + w.cat, 2 * H, B, 2 * H);
+    relu_mask_kernel<<<blocks((int64_t)B * CAT), 256, 0, stream>>>(ws + w.dcat, CAT, ws + w.dcat, CAT, ws + w.cat, CAT, B, CAT);
     // ---- action branch
-    rc = launch_gemm(ws + w.dcat, 1, 2 * H, ws + w.h1, H, 1, gr->act_fc2_w, H, H, H, B, none, ws + w.gemm, stream);
+    rc = launch_gemm(ws + w.dcat, 1, CAT, ws + w.h1, H, 1, gr->act_fc2_w, H, H, H, B, none, ws + w.gemm, stream);
     if (rc) return rc;
-    colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dcat, 2 * H, B, H, gr->act_fc2_b);
-    rc = launch_gemm(ws + w.dcat, 2 * H, 1, p->act_fc2_w, H, 1, ws + w.dh1, H, B, H, H, none, ws + w.gemm, stream);
+    colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dcat, CAT, B, H, gr->act_fc2_b);
+    rc = launch_gemm(ws + w.dcat, CAT, 1, p->act_fc2_w, H, 1, ws + w.dh1, H, B, H, H, none, ws + w.gemm, stream);
     if (rc) return rc;
     relu_mask_kernel<<<blocks((int64_t)B * H), 256, 0, stream>>>(ws + w.dh1, H, ws + w.dh1, H, ws + w.h1, H, B, H);
     rc = launch_gemm(ws + w.dh1, 1, H, ws + w.pe, 4 * d.S, 1, gr->act_fc1_w, 4 * d.S, H, 4 * d.S, B, none, ws + w.gemm, stream);
@@ -1765,11 +1798,26 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
     // ---- grid branch: Linear
     stage_mark(GNBV_ST_BWD_GRID_FC, stream);
     const float* dcat_g = ws + w.dcat + H;
-    rc = launch_gemm(dcat_g, 1, 2 * H, ws + w.act2, d.flat2, 1, gr->grid_fc_w, d.flat2, H, (int)d.flat2, B, none, ws + w.gemm, stream);
+    rc = launch_gemm(dcat_g, 1, CAT, ws + w.act2, d.flat2, 1, gr->grid_fc_w, d.flat2, H, (int)d.flat2, B, none, ws + w.gemm, stream);
     if (rc) return rc;
-    colsum_kernel<<<blocks(H), 256, 0, stream>>>(dcat_g, 2 * H, B, H, gr->grid_fc_b);
-    rc = launch_gemm(dcat_g, 2 * H, 1, p->grid_fc_w, d.flat2, 1, ws + w.dact2, d.flat2, B, (int)d.flat2, H, none, ws + w.gemm, stream);
+    colsum_kernel<<<blocks(H), 256, 0, stream>>>(dcat_g, CAT, B, H, gr->grid_fc_b);
+    rc = launch_gemm(dcat_g, CAT, 1, p->grid_fc_w, d.flat2, 1, ws + w.dact2, d.flat2, B, (int)d.flat2, H, none, ws + w.gemm, stream);
     if (rc) return rc;
+    if (sem) {
+        // semantic branch: Linear(3600, 256) then the two 2-D convolutions (dcat[:, 2H:3H] already carries the ReLU mask)
+        const float* dcat_s = ws + w.dcat + 2 * H;
+        const int FS = sem2d_flat();
+        rc = launch_gemm(dcat_s, 1, CAT, ws + w.s_out2, FS, 1, gr->rgb_fc_w, FS, H, FS, B, none, ws + w.gemm, stream);
+        if (rc) return rc;
+        colsum_kernel<<<blocks(H), 256, 0, stream>>>(dcat_s, CAT, B, H, gr->rgb_fc_b);
+        rc = launch_gemm(dcat_s, CAT, 1, p->rgb_fc_w, FS, 1, ws + w.s_dflat, FS, B, FS, H, none, ws + w.gemm, stream);
+        if (rc) return rc;
+        const int64_t rgb_off = (int64_t)state_dim + (int64_t)d.G * d.G * d.G;
+        rc = launch_sem2d_backward(obs, obs_row_stride, row_index, rgb_off, p->rgb_conv2_w, ws + w.s_out1, ws + w.s_out2, ws + w.s_dflat,
+                                   ws + w.s_dy1, ws + w.s_scratch, gr->rgb_conv1_w, gr->rgb_conv1_b, gr->rgb_conv2_w, gr->rgb_conv2_b, B,
+                                   stream);
+        if (rc) return rc;
+    }
     GNBV_LAUNCH_CHECK("linear backward");
     }
     if (!(phases & GNBV_BWD_CONV)) return GNBV_OK;

@@ -9,6 +9,12 @@ that a given torch seed yields the same initial weights.
 
 Generalisation: the reference hard-codes a 20^3 grid (`8000`, `20`, `1024`; hybrid_encoder.py:40,83-84).  Here the
 grid size is derived from the observation length: D = state_dim + G^3 + rgb_dim.
+
+`semantic_branch=True` (off by default) adds the paper's 2-D branch over the k = 2 grayscale frames that
+the observation already carries behind the grid: `naive_encoder_rgb` (Conv2d(2,16,3,s2)+ReLU, Conv2d(16,16,3,s2)+ReLU),
+`output_layer_rgb` (Linear(3600,256)+ReLU), and `output_layer` becomes Linear(768,256) -- the `[num_env, 256*3]` of
+hybrid_encoder.py:89.  The released forward never reads the frames, so this branch has no reference to pin against
+(parity unpinned; checked against torch autograd of the same layers).
 """
 import ctypes
 
@@ -51,7 +57,7 @@ class Hybrid_Encoder(nn.Module):
     RGB_DIM = 2 * 64 * 64          # k frames of 64x64 (env_train_gennbv.py:195-197), appended after the grid
 
     def __init__(self, observation_space, encoder_param=None, net_param=None, visual_input_shape=None,
-                 state_input_shape=None, grid_size=None):
+                 state_input_shape=None, grid_size=None, semantic_branch=False):
         assert encoder_param is not None, "Need parameters !"
         assert net_param is not None, "Need parameters !"
         assert isinstance(visual_input_shape, (list, tuple)), "Use tuple or list"
@@ -80,7 +86,14 @@ class Hybrid_Encoder(nn.Module):
         self.output_layer_grid = nn.Sequential(nn.Linear(self.flat2, 256), nn.ReLU(inplace=True))
         self.naive_encoder_action = nn.Sequential(nn.Linear(4 * self.state_dim, 256), nn.ReLU(inplace=True),
                                                   nn.Linear(256, 256), nn.ReLU(inplace=True))
-        self.output_layer = nn.Sequential(nn.Linear(512, 256), nn.ReLU(inplace=True))
+        self.semantic_branch = bool(semantic_branch)
+        self.output_layer = nn.Sequential(nn.Linear(768 if self.semantic_branch else 512, 256), nn.ReLU(inplace=True))
+        if self.semantic_branch:             # created last: the first 16 tensors keep the reference's RNG stream and keys
+            if obs_dim != self.state_dim + G ** 3 + self.RGB_DIM:
+                raise ValueError("semantic_branch needs the k*64*64 frame columns behind the grid in the observation")
+            self.naive_encoder_rgb = nn.Sequential(nn.Conv2d(2, 16, kernel_size=3, stride=2, padding=0), nn.ReLU(inplace=True),
+                                                   nn.Conv2d(16, 16, kernel_size=3, stride=2, padding=0), nn.ReLU(inplace=True))
+            self.output_layer_rgb = nn.Sequential(nn.Linear(16 * 15 * 15, 256), nn.ReLU(inplace=True))
         self._ws_cache = {}
         self._ws = None
         self._busy = set()                   # workspaces holding activations of a forward whose backward is pending
@@ -92,9 +105,13 @@ class Hybrid_Encoder(nn.Module):
     # order of the tensors handed to autograd (and returned by gnbv_encoder_backward)
     def _param_list(self):
         g, a = self.naive_encoder_grid, self.naive_encoder_action
-        return [g[0].weight, g[0].bias, g[1].weight, g[1].bias, g[3].weight, g[3].bias, g[4].weight, g[4].bias,
+        base = [g[0].weight, g[0].bias, g[1].weight, g[1].bias, g[3].weight, g[3].bias, g[4].weight, g[4].bias,
                 self.output_layer_grid[0].weight, self.output_layer_grid[0].bias, a[0].weight, a[0].bias,
                 a[2].weight, a[2].bias, self.output_layer[0].weight, self.output_layer[0].bias]
+        if self.semantic_branch:
+            r = self.naive_encoder_rgb
+            base += [r[0].weight, r[0].bias, r[2].weight, r[2].bias, self.output_layer_rgb[0].weight, self.output_layer_rgb[0].bias]
+        return base
 
     def _c_params(self):
         g, a = self.naive_encoder_grid, self.naive_encoder_action
@@ -105,6 +122,10 @@ class Hybrid_Encoder(nn.Module):
                  grid_fc_b=self.output_layer_grid[0].bias, act_fc1_w=a[0].weight, act_fc1_b=a[0].bias,
                  act_fc2_w=a[2].weight, act_fc2_b=a[2].bias, out_fc_w=self.output_layer[0].weight,
                  out_fc_b=self.output_layer[0].bias)
+        if self.semantic_branch:
+            r = self.naive_encoder_rgb
+            t.update(rgb_conv1_w=r[0].weight, rgb_conv1_b=r[0].bias, rgb_conv2_w=r[2].weight, rgb_conv2_b=r[2].bias,
+                     rgb_fc_w=self.output_layer_rgb[0].weight, rgb_fc_b=self.output_layer_rgb[0].bias)
         p = _lib.EncoderParams()
         for k, v in t.items():
             if not v.is_cuda or not v.is_contiguous():
@@ -134,8 +155,8 @@ class Hybrid_Encoder(nn.Module):
             raise RuntimeError("Hybrid_Encoder.forward: expected a float32 CUDA tensor [N, D] (no CPU path)")
         if obs.stride(1) != 1:
             obs = obs.contiguous()
-        if obs.shape[1] < self.state_dim + self.grid_size ** 3:
-            raise RuntimeError("observation row shorter than state + grid")
+        if obs.shape[1] < self.state_dim + self.grid_size ** 3 + (self.RGB_DIM if self.semantic_branch else 0):
+            raise RuntimeError("observation row shorter than state + grid (+ frames)")
         return obs
 
     def _run_forward(self, obs, need_bwd=False, row_index=None, training=None, feats=None):

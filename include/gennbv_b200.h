@@ -27,7 +27,7 @@ extern "C" {
 #define GNBV_E_CUDA (-2)     /* a CUDA runtime call / kernel launch failed */
 #define GNBV_E_WORKSPACE (-3) /* workspace too small */
 
-#define GNBV_ABI_VERSION 2
+#define GNBV_ABI_VERSION 3
 
 int gnbv_abi_version(void);
 /* Kernel variants in effect for this process: which = 0 -> GNBV_CONV2_TC, 1 -> GNBV_CONV1_MMA, 2 -> GNBV_GEMM_MMA
@@ -206,6 +206,11 @@ typedef struct gnbv_encoder_params {
     float *bn2_rm, *bn2_rv;
     int64_t* bn2_nbt;
     const float *grid_fc_w, *grid_fc_b, *act_fc1_w, *act_fc1_b, *act_fc2_w, *act_fc2_b, *out_fc_w, *out_fc_b;
+    /* Optional 2-D semantic branch (all NULL = off, the released architecture): Conv2d(2,16,3,s2)+ReLU ->
+     * Conv2d(16,16,3,s2)+ReLU -> Flatten -> Linear(3600,256)+ReLU on the k = 2 grayscale 64x64 frames stored behind the grid
+     * columns of the observation row; out_fc_w is then [256, 768] (action | grid | semantic).  Parity unpinned: the reference's
+     * forward has no such branch (hybrid_encoder.py:69-91) and the paper gives no layer sizes. */
+    const float *rgb_conv1_w, *rgb_conv1_b, *rgb_conv2_w, *rgb_conv2_b, *rgb_fc_w, *rgb_fc_b;
 } gnbv_encoder_params;
 
 /* Workspace (bytes) for a forward (with_backward = 0) or forward + backward (1) of `batch` rows. */
@@ -242,6 +247,7 @@ int gnbv_debug_ts_profile(unsigned long long* out32);
 typedef struct gnbv_encoder_grads {
     float *conv1_w, *conv1_b, *bn1_w, *bn1_b, *conv2_w, *conv2_b, *bn2_w, *bn2_b;
     float *grid_fc_w, *grid_fc_b, *act_fc1_w, *act_fc1_b, *act_fc2_w, *act_fc2_b, *out_fc_w, *out_fc_b;
+    float *rgb_conv1_w, *rgb_conv1_b, *rgb_conv2_w, *rgb_conv2_b, *rgb_fc_w, *rgb_fc_b;      /* semantic branch, or NULL */
 } gnbv_encoder_grads;
 
 /* Backward of gnbv_encoder_forward on the same `workspace` (allocated with with_backward = 1 and untouched since the

@@ -14,9 +14,9 @@ ACTION_NVEC = (81, 81, 51, 1, 13, 13)
 
 
 class HybridEncoderRef(nn.Module):
-    def __init__(self, grid_size=20, state_dim=600, features_dim=256):
+    def __init__(self, grid_size=20, state_dim=600, features_dim=256, semantic=False):
         super().__init__()
-        self.G, self.state_dim, self.features_dim = grid_size, state_dim, features_dim
+        self.G, self.state_dim, self.features_dim, self.semantic = grid_size, state_dim, features_dim, semantic
         g1 = (grid_size - 3) // 2 + 1
         g2 = (g1 - 3) // 2 + 1
         self.naive_encoder_grid = nn.Sequential(
@@ -25,7 +25,13 @@ class HybridEncoderRef(nn.Module):
         self.output_layer_grid = nn.Sequential(nn.Linear(16 * g2 ** 3, 256), nn.ReLU(inplace=True))
         self.naive_encoder_action = nn.Sequential(nn.Linear(4 * state_dim, 256), nn.ReLU(inplace=True),
                                                   nn.Linear(256, 256), nn.ReLU(inplace=True))
-        self.output_layer = nn.Sequential(nn.Linear(512, features_dim), nn.ReLU(inplace=True))
+        self.output_layer = nn.Sequential(nn.Linear(768 if semantic else 512, features_dim), nn.ReLU(inplace=True))
+        if semantic:
+            # 2-D branch over the k = 2 grayscale 64x64 frames behind the grid.  No reference forward exists
+            # for it (hybrid_encoder.py:69-91 never reads the frames): PARITY UNPINNED, layer sizes are this build's choice.
+            self.naive_encoder_rgb = nn.Sequential(nn.Conv2d(2, 16, kernel_size=3, stride=2, padding=0), nn.ReLU(inplace=True),
+                                                   nn.Conv2d(16, 16, kernel_size=3, stride=2, padding=0), nn.ReLU(inplace=True))
+            self.output_layer_rgb = nn.Sequential(nn.Linear(16 * 15 * 15, 256), nn.ReLU(inplace=True))
 
     @staticmethod
     def positional_encoding(positions, freqs=2):
@@ -39,16 +45,20 @@ class HybridEncoderRef(nn.Module):
         fa = self.naive_encoder_action(self.positional_encoding(a).view(n, -1))
         g = obs[:, self.state_dim:self.state_dim + G ** 3].reshape(n, 1, G, G, G)
         fg = self.output_layer_grid(self.naive_encoder_grid(g).reshape(n, -1))
-        return self.output_layer(torch.cat((fa, fg), dim=-1))
+        if not self.semantic:
+            return self.output_layer(torch.cat((fa, fg), dim=-1))
+        r = obs[:, self.state_dim + G ** 3:self.state_dim + G ** 3 + 2 * 64 * 64].reshape(n, 2, 64, 64)
+        fr = self.output_layer_rgb(self.naive_encoder_rgb(r).reshape(n, -1))
+        return self.output_layer(torch.cat((fa, fg, fr), dim=-1))
 
 
 class PolicyRef(nn.Module):
     """ActorCriticPolicy_Train_Eval with net_arch=[] (policies.py:954-1090): heads directly on the encoder output."""
 
-    def __init__(self, grid_size=20, state_dim=600, nvec=ACTION_NVEC):
+    def __init__(self, grid_size=20, state_dim=600, nvec=ACTION_NVEC, semantic=False):
         super().__init__()
         self.nvec = tuple(nvec)
-        self.features_extractor = HybridEncoderRef(grid_size, state_dim)
+        self.features_extractor = HybridEncoderRef(grid_size, state_dim, semantic=semantic)
         self.action_net = nn.Linear(256, sum(nvec))
         self.value_net = nn.Linear(256, 1)
 

@@ -88,7 +88,7 @@ def main():
         "history_keys_per_env": {"min": min(counts), "mean": sum(counts) / E, "max": max(counts)},
         "dedup_points_per_env": {"min": min(sizes), "mean": sum(sizes) / E, "max": max(sizes)},
         "eval_env_step_ms": {"median": sorted(step_ms)[len(step_ms) // 2], "includes": "sensor synthesis + env.step + history append"},
-        "dedup_decode_ms_all_envs": dedup_ms, "dedup_how": "one torch.unique over env-tagged keys + one decode launch",
+        "dedup_decode_ms_all_envs": dedup_ms, "dedup_how": "gnbv_pack_env_keys + in-tree radix sort / unique (gnbv_sort_unique_u64) + one decode launch",
         "chamfer_grid_ms_all_envs": grid_ms,
         "cells_per_axis": C,
         "accuracy": {"min": float((cx + cy).min()), "mean": float((cx + cy).mean()), "max": float((cx + cy).max())},

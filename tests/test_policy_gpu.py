@@ -75,20 +75,28 @@ def oracle_grads(ref, obs, wsum, training, dtype, masks=None):
         x = o[:, m.state_dim:m.state_dim + G ** 3].reshape(n, 1, G, G, G)
         x = seq[1](seq[0](x)) * masks[0].to(dtype)
         x = seq[4](seq[3](x)) * masks[1].to(dtype)
-        f = m.output_layer(torch.cat((fa, m.output_layer_grid(x.reshape(n, -1))), dim=-1))
+        parts = [fa, m.output_layer_grid(x.reshape(n, -1))]
+        if m.semantic:
+            r = o[:, m.state_dim + G ** 3:m.state_dim + G ** 3 + 8192].reshape(n, 2, 64, 64)
+            parts.append(m.output_layer_rgb(m.naive_encoder_rgb(r).reshape(n, -1)))
+        f = m.output_layer(torch.cat(parts, dim=-1))
     (f * wsum.to(dtype)).sum().backward()
     return f.detach(), {k: p.grad.detach() for k, p in m.named_parameters()}, {k: b.detach().clone() for k, b in m.named_buffers()}
 
 
-def make_policy(G, seed, state_dim=600):
+def make_policy(G, seed, state_dim=600, semantic=False):
     D = state_dim + G ** 3 + 2 * 64 * 64
     kwargs = dict(encoder_param={"hidden_shapes": [256, 256], "visual_dim": 256},
                   net_param={"transformer_params": [[1, 256], [1, 256]], "append_hidden_shapes": [256, 256]},
                   state_input_shape=(state_dim,), visual_input_shape=(100, 48, 48))
+    if semantic:
+        kwargs["semantic_branch"] = True
     pol = ActorCriticPolicy_Train_Eval(Box(-np.inf, np.inf, (D,), np.float32), MultiDiscrete([81, 81, 51, 1, 13, 13]),
                                        lambda _: 1e-4, net_arch=[], features_extractor_kwargs=kwargs, device=DEV)
-    ref = encoder_ref.PolicyRef(G, state_dim)
+    ref = encoder_ref.PolicyRef(G, state_dim, semantic=semantic)
     sd = encoder_ref.seeded_state_dict(ref, seed)
+    if semantic:
+        sd["features_extractor.naive_encoder_rgb.0.weight"] /= 255.0        # frames are 0..255 gray levels
     ref.load_state_dict(sd)
     pol.load_state_dict(sd)
     return pol, ref, D
@@ -191,7 +199,19 @@ def test_policy_matches_reference_golden_g20():
 # persistent-block / work-item splitting of every conv kernel depends on B
 @pytest.mark.parametrize("G,B,seed", [(20, 9, 1), (32, 5, 2), (64, 3, 3), (21, 4, 4), (64, 128, 5), (64, 256, 6)])
 def test_encoder_forward_backward_vs_torch(G, B, seed):
-    pol, ref, D = make_policy(G, seed)
+    _encoder_parity(G, B, seed, semantic=False)
+
+
+# the 2-D semantic branch (off by default).  PARITY UNPINNED -- the reference's forward has no such branch; the
+# kernels (csrc/sem2d.cu) are checked against torch autograd of the same layers (oracle/encoder_ref.py, semantic=True)
+@pytest.mark.parametrize("G,B,seed", [(20, 6, 11), (64, 3, 12), (20, 130, 13)])
+def test_semantic_branch_forward_backward_vs_torch(G, B, seed):
+    _encoder_parity(G, B, seed, semantic=True)
+
+
+def _encoder_parity(G, B, seed, semantic):
+    pol, ref, D = make_policy(G, seed, semantic=semantic)
+    assert len(pol.features_extractor._param_list()) == (22 if semantic else 16)
     g = torch.Generator().manual_seed(seed)
     obs = torch.zeros(B, D)
     obs[:, :600] = torch.randn(B, 600, generator=g) * 3

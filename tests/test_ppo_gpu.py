@@ -21,12 +21,17 @@ POLICY_KW = lambda: dict(net_arch=[], features_extractor_kwargs=dict(
     state_input_shape=(600,), visual_input_shape=(100, 48, 48)))
 
 
-def make_algo(env, n_steps, batch_size, n_epochs, target_kl=None, seed=3):
+def make_algo(env, n_steps, batch_size, n_epochs, target_kl=None, seed=3, semantic=False):
+    kw = POLICY_KW()
+    if semantic:
+        kw["features_extractor_kwargs"]["semantic_branch"] = True
     algo = PPO_Grid_Obs(env=env, learning_rate=1e-4, n_steps=n_steps, batch_size=batch_size, n_epochs=n_epochs, gamma=0.99,
                         gae_lambda=0.95, clip_range=0.2, clip_range_vf=0.2, ent_coef=0.01, vf_coef=0.8, max_grad_norm=1,
-                        target_kl=target_kl, policy_kwargs=POLICY_KW(), seed=seed, device=DEV)
-    ref = encoder_ref.PolicyRef(env.grid_size, 600)
+                        target_kl=target_kl, policy_kwargs=kw, seed=seed, device=DEV)
+    ref = encoder_ref.PolicyRef(env.grid_size, 600, semantic=semantic)
     sd = encoder_ref.seeded_state_dict(ref, seed, scale=0.5)
+    if semantic:
+        sd["features_extractor.naive_encoder_rgb.0.weight"] /= 255.0        # frames are 0..255 gray levels
     ref.load_state_dict(sd)
     algo.policy.load_state_dict(sd)
     return algo, ref
@@ -194,6 +199,23 @@ def test_fused_train_matches_torch_rerun(target_kl, graph):
     _check_train_against_rerun(algo, ref, before, logs, steps, last_kl)
     if graph:
         assert len(algo._graphs) >= 1, "the minibatch update was expected to run as a captured CUDA graph"
+
+
+def test_fused_train_with_the_semantic_branch_matches_torch_rerun():
+    """the whole update (rollout, captured minibatch graph, clip + Adam over the 26-tensor arena) with the 2-D
+    branch switched on, against the plain-PyTorch re-run of the reference's train() lines over the same three-branch network."""
+    g = EnvGolden("env_g20_long")
+    env = EnvWrapperGenNBVTrain(make_env(g))
+    T, B, E = 8, 12, 2
+    algo, ref = make_algo(env, n_steps=T, batch_size=B, n_epochs=E, semantic=True)
+    assert len(algo.policy.arena_parameters()) == 26
+    algo._setup_learn()
+    algo.collect_rollouts()
+    logs, steps, last_kl, stop = _torch_rerun(ref, algo.rollout_buffer, g.N, T, B, E, None)
+    before = {k: v.clone() for k, v in algo.policy.state_dict().items()}
+    algo.train()
+    _check_train_against_rerun(algo, ref, before, logs, steps, last_kl)
+    assert len(algo._graphs) >= 1
 
 
 def test_graph_and_eager_updates_are_bit_identical():
