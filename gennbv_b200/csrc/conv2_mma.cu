@@ -556,13 +556,21 @@ conv2_wgrad_mma_kernel(const float* __restrict__ y1, const float* __restrict__ s
 // t+4 <-> (row t, z+1).  With that choice the four t-lanes of a fragment load read four DIFFERENT staged lines, and the
 // line pitch is padded to 4 (mod 32) floats (dy2 lines: 8 mod 32), so the 32 lanes of every LDS hit 32 different banks
 // -- positions of one line alone are always 32 floats apart and would collide four ways.
-// The 54 n-tiles (27 taps x 2 channel halves) are dealt round-robin to the 16 warps (<= 4 each = 16 accumulators); with one
-// block per SM (120 KB of stages) that is 4 warps per scheduler -- at 8 warps (2 per scheduler) the dependent
-// LDS -> BN/ReLU -> split -> HMMA chains were not covered (measured 0.50 ms, tensor pipe 30 % busy).
-constexpr int WGS_THREADS = 512;
-constexpr int WGS_WARPS = WGS_THREADS / 32;
-constexpr int WGS_NT = (2 * NTAPS + WGS_WARPS - 1) / WGS_WARPS;      // 7 n-tiles per warp
+// The 54 n-tiles (27 taps x 2 channel halves) are dealt round-robin to 18 consumer warps, exactly 3 each.  A 19th warp is the
+// producer: its lanes issue the <= 31 bulk copies of a group in parallel and it alone waits for a stage to drain.  Stages are
+// handed over through mbarriers in both directions (full: TMA bytes landed; empty: 18 warp arrivals), so there is no
+// block-wide barrier in the loop and a warp that finishes a group early starts the next one.
+// (Round-2 profile of the previous 16-warp form, where thread 0 issued the copies and 6 warps carried a 4th n-tile: 33 % of all
+// warp samples were stall_barrier at the per-group __syncthreads; profiles/r02n_*.)
+constexpr int WGS_WARPS = 18;                                        // consumer warps
+constexpr int WGS_THREADS = (WGS_WARPS + 1) * 32;                    // + the producer warp
+constexpr int WGS_NT = 2 * NTAPS / WGS_WARPS;                        // 3 n-tiles per warp
+static_assert(WGS_NT * WGS_WARPS == 2 * NTAPS && WGS_WARPS % 2 == 0, "n-tiles must deal evenly, keeping the channel half per warp");
 constexpr int WGS_ROWS = 4;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
 
 __host__ __device__ inline int pad_mod32(int n, int r) {             // smallest multiple-of-4 value >= n that is r (mod 32)
     int v = (n / 32) * 32 + r;
@@ -573,8 +581,8 @@ __global__ void __launch_bounds__(WGS_THREADS, 1)
 conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, const float* __restrict__ dy2cl,
                           float* __restrict__ part, int G1, int G2, int total_groups, int groups_per_block) {
     extern __shared__ __align__(128) float dsm[];
-    __shared__ __align__(8) uint64_t mbar[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    __shared__ __align__(8) uint64_t mbar[2], mbar_empty[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), g = lane >> 2, t = lane & 3;
     const int P1 = G1 * G1 * G1, P2 = G2 * G2 * G2;
     const int LP = pad_mod32(G1 * C, 4), DP = pad_mod32(G2 * C, 8);         // floats per staged y1 / dy2 line
     const int STAGE = 27 * LP + WGS_ROWS * DP;
@@ -584,6 +592,7 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
     // (n-tile nt = warp + 16k <-> tap nt >> 1, channel half nt & 1 = warp & 1: a warp only ever sees one channel half)
     const int hf = warp & 1;
     const float scv = stat1[2 * C + 8 * hf + g], shv = stat1[3 * C + 8 * hf + g];
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]), empty0 = (uint32_t)__cvta_generic_to_shared(&mbar_empty[0]);
     // acc: the MMA accumulators of ONE group; tot: their running sum over the block's groups, added with ordinary
     // round-to-nearest FADDs.  The tensor core's fp32 accumulation truncates, so a chain of thousands of MMAs into one
     // register drifts (measured 5e-4 relative at B = 128 on the conv1 twin of this kernel); 24 MMAs per chain do not.
@@ -592,7 +601,11 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
     for (int k = 0; k < WGS_NT; ++k) { tot[k][0] = tot[k][1] = tot[k][2] = tot[k][3] = 0.f; }
     float db_lo = 0.f, db_hi = 0.f;
     const int g0 = blockIdx.x * groups_per_block, g1 = min(total_groups, g0 + groups_per_block);
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_init_fence(); }
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1);
+        mbar_init(&mbar_empty[0], WGS_WARPS); mbar_init(&mbar_empty[1], WGS_WARPS);
+        mbar_init_fence();
+    }
     __syncthreads();
     auto decode = [&](int grp, int& b, int& x2, int& y20, int& nrows) {
         b = grp / (G2 * NYG);
@@ -601,30 +614,38 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
         y20 = (rem - x2 * NYG) * WGS_ROWS;
         nrows = min(WGS_ROWS, G2 - y20);
     };
-    auto issue = [&](int grp, int stage) {                  // thread 0 only
+    auto issue = [&](int grp, int stage) {                  // the whole producer warp: one bulk copy per lane
         int b, x2, y20, nrows;
         decode(grp, b, x2, y20, nrows);
         const int nlines = 2 * nrows + 1;                   // input y-lines 2*y20 .. 2*y20 + 2*nrows
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&mbar[stage]);
+        const uint32_t bar = full0 + 8u * stage;
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(dsm + stage * STAGE);
-        mbar_expect_tx(bar, 3 * nlines * line_bytes + nrows * dy_bytes);
-        for (int i = 0; i < 3; ++i)
-            for (int yl = 0; yl < nlines; ++yl)
-                bulk_g2s(dst + (uint32_t)((i * 9 + yl) * LP * 4),
-                         y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2 + i) * G1 + (2 * y20 + yl)) * G1) * C, line_bytes, bar);
-        for (int r = 0; r < nrows; ++r)
+        if (lane == 0) mbar_expect_tx(bar, 3 * nlines * line_bytes + nrows * dy_bytes);
+        __syncwarp();
+        if (lane < 3 * nlines) {
+            const int i = lane / nlines, yl = lane - i * nlines;
+            bulk_g2s(dst + (uint32_t)((i * 9 + yl) * LP * 4),
+                     y1 + ((int64_t)b * P1 + ((int64_t)(2 * x2 + i) * G1 + (2 * y20 + yl)) * G1) * C, line_bytes, bar);
+        } else if (lane - 3 * nlines < nrows) {
+            const int r = lane - 3 * nlines;
             bulk_g2s(dst + (uint32_t)((27 * LP + r * DP) * 4), dy2cl + ((int64_t)b * P2 + (int64_t)(x2 * G2 + y20 + r) * G2) * C,
                      dy_bytes, bar);
+        }
     };
-    if (tid == 0 && g0 < g1) issue(g0, 0);
-    uint32_t phase[2] = {0, 0};
     bool ok = true;
+    if (warp == WGS_WARPS) {                                // ---- producer warp ----
+        for (int grp = g0; grp < g1; ++grp) {
+            const int j = grp - g0, stage = j & 1;
+            if (j >= 2) ok = mbar_wait_parity(empty0 + 8u * stage, (uint32_t)(((j >> 1) - 1) & 1)) && ok;   // drained by all 18 warps
+            issue(grp, stage);
+        }
+        if (!ok) { asm volatile("trap;"); }
+        return;
+    }
     const int nzp = (G2 + 1) / 2;
     for (int grp = g0; grp < g1; ++grp) {
-        const int stage = (grp - g0) & 1;
-        if (tid == 0 && grp + 1 < g1) issue(grp + 1, stage ^ 1);     // stage^1 was released by the barrier ending grp-1
-        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
-        phase[stage] ^= 1;
+        const int j = grp - g0, stage = j & 1;
+        ok = mbar_wait_parity(full0 + 8u * stage, (uint32_t)((j >> 1) & 1)) && ok;
         int b, x2, y20, nrows;
         decode(grp, b, x2, y20, nrows);
         const float* xs = dsm + stage * STAGE;
@@ -666,7 +687,8 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
         }
 #pragma unroll
         for (int k = 0; k < WGS_NT; ++k) { tot[k][0] += acc[k][0]; tot[k][1] += acc[k][1]; tot[k][2] += acc[k][2]; tot[k][3] += acc[k][3]; }
-        __syncthreads();                                    // everyone is done with this stage before it is refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8u * stage);    // this warp is done with the stage (the producer refills it after all 18)
     }
     if (!ok) { asm volatile("trap;"); }
     float* out = part + (int64_t)blockIdx.x * WG_REC;

@@ -97,7 +97,9 @@ __device__ __forceinline__ int pixel_to_voxel(const EnvGeom& g, float d, float u
 
 // number of secondary-axis increments after n Bresenham iterations (see raycast())
 __device__ __forceinline__ int bres_steps(int d_minor, int d_major, int n) {
-    return (int)((2LL * d_minor * n + d_major) / (2LL * d_major));
+    const long long num = 2LL * d_minor * n + d_major;
+    if (num < 0x7fffffffLL && d_major < 0x3fffffff) return (int)((unsigned)num / (unsigned)(2 * d_major));   // the usual case: 32-bit divide
+    return (int)(num / (2LL * d_major));
 }
 
 // gennbv/utils.py:48-167 for one ray, marking the touched mask instead of writing a trajectory.
@@ -213,48 +215,53 @@ scan_raycast_kernel(const float* __restrict__ depth, const int32_t* __restrict__
     }
     __syncthreads();
 
-    // ---- phase 2: compact targets, ray-cast --------------------------------------------------
-    // blocked ownership: thread t owns words [t*wpt, (t+1)*wpt)
-    const int wpt = (words + K1_THREADS - 1) / K1_THREADS;
-    const int w_begin = min(tid * wpt, words), w_end = min(w_begin + wpt, words);
+    // ---- phase 2: compact targets (ascending voxel index), ray-cast --------------------------------
+    // Warp-cooperative compaction: warp w owns the words [w*wpw, (w+1)*wpw); lanes read 32 consecutive words at a time.  Every
+    // non-empty word is expanded by the whole warp at once (lane j owns bit j), so the cost follows the number of non-empty
+    // words, not the longest run of set bits a single thread happens to own.  Neighbouring list entries are neighbouring
+    // voxels: the 32 rays of a warp walk nearly the same cells, which keeps the shared-memory reads of the walk conflict-free.
+    const int wpw = (words + K1_WARPS - 1) / K1_WARPS;
+    const int w_begin = min(warp * wpw, words), w_end = min(w_begin + wpw, words);
     int cnt = 0;
-    for (int w = w_begin; w < w_end; ++w) cnt += __popc(tmask[w]);
-    int incl = cnt;
+    for (int w = w_begin + lane; w < w_end; w += 32) cnt += __popc(tmask[w]);
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) warp_tot[warp] = cnt;
     __syncthreads();
     if (warp == 0) {
-        int t = warp_tot[lane];
+        int t = lane < K1_WARPS ? warp_tot[lane] : 0;
         int s = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             int q = __shfl_up_sync(0xffffffffu, s, o);
             if (lane >= o) s += q;
         }
-        warp_tot[lane] = s - t;                  // exclusive
+        if (lane < K1_WARPS) warp_tot[lane] = s - t;      // exclusive
         if (lane == 31) total_targets = s;
     }
     __syncthreads();
-    const int my_base = warp_tot[warp] + incl - cnt;
+    const int my_base = warp_tot[warp];
     const int total = total_targets;
     if (tid == 0 && num_targets) num_targets[n] = total;
 
     const int sx0 = src[0], sy0 = src[1], sz0 = src[2];
     for (int round = 0; round * LIST_CAP < total; ++round) {
         const int win_lo = round * LIST_CAP, win_hi = min(total, win_lo + LIST_CAP);
-        int rank = my_base;
-        if (rank < win_hi && rank + cnt > win_lo) {
-            for (int w = w_begin; w < w_end; ++w) {
-                uint32_t bits = tmask[w];
-                while (bits) {
-                    int b = __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    if (rank >= win_lo && rank < win_hi) list[rank - win_lo] = (uint32_t)(w * 32 + b);
-                    ++rank;
+        if (my_base < win_hi && my_base + cnt > win_lo) {
+            int rank = my_base;
+            for (int w0 = w_begin; w0 < w_end; w0 += 32) {
+                const int w = w0 + lane;
+                const uint32_t mine = w < w_end ? tmask[w] : 0u;
+                unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+                while (nz) {
+                    const int srcl = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    const uint32_t wd = __shfl_sync(0xffffffffu, mine, srcl);
+                    if ((wd >> lane) & 1u) {
+                        const int pos = rank + __popc(wd & ((1u << lane) - 1u));
+                        if (pos >= win_lo && pos < win_hi) list[pos - win_lo] = (uint32_t)((w0 + srcl) * 32 + lane);
+                    }
+                    rank += __popc(wd);
                 }
             }
         }

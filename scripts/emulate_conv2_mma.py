@@ -384,14 +384,14 @@ def pad_mod32(n, r):
 
 def wgrad_staged(y1, sc, sh, dy2cl, G1, G2, B, nblocks):
     """conv2_wgrad_staged_kernel: groups of 4 output rows staged as 27 y1 lines + 4 dy2 lines; slot t <-> (row t, z),
-    slot t+4 <-> (row t, z+1); n-tiles dealt round-robin to 16 warps."""
+    slot t+4 <-> (row t, z+1); n-tiles dealt round-robin to the 18 consumer warps (3 each)."""
     P1, P2 = G1 ** 3, G2 ** 3
     LP, DP = pad_mod32(G1 * C, 4), pad_mod32(G2 * C, 8)
     NYG = -(-G2 // 4)
     total = B * G2 * NYG
     gpb = -(-total // nblocks)
     nblk = -(-total // gpb)
-    NW = 16
+    NW = 18
     NTW = -(-2 * NT // NW)
     rec = np.zeros((nblk, C * C * NT + C))
     nzp = (G2 + 1) // 2

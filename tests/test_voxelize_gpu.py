@@ -81,6 +81,30 @@ def test_against_oracle(N, H, W, G, S, seed):
         np.testing.assert_array_equal(scan_c, scan_o)
 
 
+def test_more_distinct_targets_than_the_ray_list_holds(seed=31):
+    """The kernel lists distinct targets while it scatters them (8192 slots); past that it rebuilds the list from the target
+    mask in rounds.  Every pixel foreground with a random depth across the grid's bounding sphere: > 8192 distinct voxels."""
+    N, H, W, G = 2, 512, 512, 64
+    c = synthetic_case(N, H, W, G, 2, seed, steps=1)
+    depth, seg, c2w, xyz = c["frames"][0]
+    rng = np.random.default_rng(seed)
+    rg = c["range_gt"]
+    ctr = np.stack([(rg[:, 0] + rg[:, 1]) / 2, (rg[:, 2] + rg[:, 3]) / 2, (rg[:, 4] + rg[:, 5]) / 2], 1)
+    R = np.abs(np.stack([rg[:, 0] - rg[:, 1], rg[:, 2] - rg[:, 3], rg[:, 4] - rg[:, 5]], 1)).max(1) / 2
+    dist = np.linalg.norm(xyz - ctr, axis=1)
+    depth = -np.abs((dist - R)[:, None, None] + rng.uniform(0, 1, depth.shape) * (2 * R)[:, None, None]).astype(np.float32)
+    seg = np.full_like(seg, 255)
+    prob_o = np.zeros((N, G, G, G), np.float32); scan_o = np.zeros_like(prob_o)
+    prob_c = np.zeros_like(prob_o); scan_c = np.zeros_like(prob_o)
+    o = c_oracle.voxelize_step(depth, seg, c["kinv"], c2w, c["range_gt"], c["vs"], xyz, c["grid_gt"], prob_o, scan_o,
+                               raw_depth=True, want_masks=True)
+    k = cuda_step(depth, seg, c["kinv"], c2w, c["range_gt"], c["vs"], xyz, c["grid_gt"], prob_c, scan_c, True, True)
+    assert int(o["num_targets"].min()) > 8192, o["num_targets"]
+    for key in ("num_targets", "target_mask", "touched_mask", "tri", "cov_sum"):
+        np.testing.assert_array_equal(k[key], o[key], err_msg=key)
+    np.testing.assert_array_equal(prob_c, prob_o)
+
+
 def test_ray_sources_inside_behind_and_far(seed=21):
     """Bresenham entry logic: camera voxel inside the grid, on a face, far away (|idx| ~ 1e5), equal to a target."""
     N, H, W, G = 8, 64, 64, 32
