@@ -568,9 +568,6 @@ constexpr int WGS_NT = 2 * NTAPS / WGS_WARPS;                        // 3 n-tile
 static_assert(WGS_NT * WGS_WARPS == 2 * NTAPS && WGS_WARPS % 2 == 0, "n-tiles must deal evenly, keeping the channel half per warp");
 constexpr int WGS_ROWS = 4;
 
-__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
-}
 
 __host__ __device__ inline int pad_mod32(int n, int r) {             // smallest multiple-of-4 value >= n that is r (mod 32)
     int v = (n / 32) * 32 + r;

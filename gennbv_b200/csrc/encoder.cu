@@ -1108,15 +1108,20 @@ __device__ __forceinline__ uint32_t conv1_wgrad_mma_rowblock(const float* __rest
     return orbits & 0x1fffu;
 }
 
+// 8 consumer warps + a producer warp (lane 0 issues the five bulk copies of a row block and alone waits for a stage to drain);
+// stages are handed over by mbarriers in both directions, so the loop has no block-wide barrier -- the 16-warp-barrier form spent
+// 21 % of its warp samples in stall_barrier (profiles/r02n_*).  The TF32-exactness fallback is decided per warp: a warp's
+// accumulators depend only on the k-steps it multiplied itself.
+constexpr int WG1M_THREADS = C1M_THREADS + 32;
 template <int RB>
-__global__ void __launch_bounds__(C1M_THREADS, 2)
+__global__ void __launch_bounds__(WG1M_THREADS, 2)
 conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
                        const float* __restrict__ g1, const float* __restrict__ y1, const float* __restrict__ stat1,
                        const float* __restrict__ coef, float* __restrict__ part, int G, int G1, int total_rb, int rb_per_block) {
     extern __shared__ __align__(128) float dsm[];
     __shared__ float red[C1M_WARPS][WG1_REC];
-    __shared__ __align__(8) uint64_t mbar[2];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+    __shared__ __align__(8) uint64_t mbar[2], mbar_empty[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = __shfl_sync(0xffffffffu, tid >> 5, 0), g = lane >> 2, t = lane & 3;
     const int P1 = G1 * G1 * G1, NYB = (G1 + RB - 1) / RB;
     const int TL = (2 * RB + 1) * G;                    // floats per staged tri slab
     const int GL = RB * G1 * C1;                        // floats per staged g1 / y1 slab
@@ -1144,6 +1149,8 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        mbar_init(&mbar_empty[0], C1M_WARPS);
+        mbar_init(&mbar_empty[1], C1M_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1169,35 +1176,44 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
         bulk_g2s(dst + (uint32_t)(3 * TL * 4), g1 + goff, g_bytes, bar);
         bulk_g2s(dst + (uint32_t)((3 * TL + GL) * 4), y1 + goff, g_bytes, bar);
     };
-    if (tid == 0 && rb0 < rb1) issue(rb0, 0);
-    uint32_t phase[2] = {0, 0};
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]), empty0 = (uint32_t)__cvta_generic_to_shared(&mbar_empty[0]);
     bool ok = true;
-    for (int rb = rb0; rb < rb1; ++rb) {
-        const int stage = (rb - rb0) & 1;
-        if (tid == 0 && rb + 1 < rb1) issue(rb + 1, stage ^ 1);
-        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
-        phase[stage] ^= 1;
-        int b, x1, y0, nr;
-        decode(rb, b, x1, y0, nr);
-        const float* ts = dsm + stage * STAGE;
-        const float* gs = ts + 3 * TL;
-        const float* ys = gs + GL;
-        const float keep_db[2] = {dbs[0], dbs[1]};
+    if (wid == C1M_WARPS) {                                 // ---- producer warp ----
+        if (lane == 0)
+            for (int rb = rb0; rb < rb1; ++rb) {
+                const int j = rb - rb0, stage = j & 1;
+                if (j >= 2) ok = mbar_wait_parity(empty0 + 8u * stage, (uint32_t)(((j >> 1) - 1) & 1)) && ok;
+                issue(rb, stage);
+            }
+        __syncwarp();
+    } else {
+        for (int rb = rb0; rb < rb1; ++rb) {
+            const int j = rb - rb0, stage = j & 1;
+            ok = mbar_wait_parity(full0 + 8u * stage, (uint32_t)((j >> 1) & 1)) && ok;
+            int b, x1, y0, nr;
+            decode(rb, b, x1, y0, nr);
+            const float* ts = dsm + stage * STAGE;
+            const float* gs = ts + 3 * TL;
+            const float* ys = gs + GL;
+            const float keep_db[2] = {dbs[0], dbs[1]};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-        const uint32_t inexact = conv1_wgrad_mma_rowblock<false>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
-        if (__syncthreads_or((int)inexact)) {               // some input value is not a TF32 number: redo with B split
+            for (int j2 = 0; j2 < 4; ++j2) { acc[j2][0] = acc[j2][1] = acc[j2][2] = acc[j2][3] = 0.f; }
+            const uint32_t inexact = conv1_wgrad_mma_rowblock<false>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
+            if (__any_sync(0xffffffffu, inexact != 0u)) {       // this warp met an input value that is not a TF32 number: redo with B split
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-            dbs[0] = keep_db[0]; dbs[1] = keep_db[1];
-            conv1_wgrad_mma_rowblock<true>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
+                for (int j2 = 0; j2 < 4; ++j2) { acc[j2][0] = acc[j2][1] = acc[j2][2] = acc[j2][3] = 0.f; }
+                dbs[0] = keep_db[0]; dbs[1] = keep_db[1];
+                conv1_wgrad_mma_rowblock<true>(ts, gs, ys, G, G1, TL, nr, kc, boff, acc, dbs);
+            }
+#pragma unroll
+            for (int j2 = 0; j2 < 4; ++j2) { tot[j2][0] += acc[j2][0]; tot[j2][1] += acc[j2][1]; tot[j2][2] += acc[j2][2]; tot[j2][3] += acc[j2][3]; }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * stage);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { tot[j][0] += acc[j][0]; tot[j][1] += acc[j][1]; tot[j][2] += acc[j][2]; tot[j][3] += acc[j][3]; }
-        __syncthreads();
     }
     if (!ok) { asm volatile("trap;"); }
     // accumulators: c0 (co g, tap 8j+2t), c1 (co g, tap 8j+2t+1), c2 (co g+8, tap 8j+2t), c3 (co g+8, tap 8j+2t+1)
+    if (wid < C1M_WARPS) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -1211,8 +1227,9 @@ conv1_wgrad_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const 
         d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
         if (t == 0) { red[wid][C1 * TAPS + g] = d0; red[wid][C1 * TAPS + 8 + g] = d1; }
     }
+    }
     __syncthreads();
-    for (int j = tid; j < WG1_REC; j += C1M_THREADS) {
+    for (int j = tid; j < WG1_REC; j += WG1M_THREADS) {
         float tsum = 0.f;
 #pragma unroll
         for (int w = 0; w < C1M_WARPS; ++w) tsum += red[w][j];
@@ -1299,14 +1316,18 @@ __device__ __forceinline__ uint32_t conv1_mma_rowblock(const float* __restrict__
     return orbits & 0x1fffu;
 }
 
-__global__ void __launch_bounds__(C1M_THREADS)
+// 8 consumer warps + a producer warp; stages handed over by mbarriers in both directions (no block barrier per row block), the
+// exactness fallback decided per warp, and ONE BatchNorm partial record per block (shifted sums kept in registers across the
+// block's row blocks) instead of a block-wide merge per row block.
+constexpr int C1F_THREADS = C1M_THREADS + 32;
+__global__ void __launch_bounds__(C1F_THREADS, 2)
 conv1_fwd_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const int64_t* __restrict__ rows, int64_t grid_off,
                      const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ y1,
                      float* __restrict__ part, int G, int G1, int RBF, int total_rb, int rb_per_block) {
     extern __shared__ __align__(128) float dsm[];
     __shared__ float red[C1M_WARPS][3 * C1];
-    __shared__ __align__(8) uint64_t mbar[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    __shared__ __align__(8) uint64_t mbar[2], mbar_empty[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), g = lane >> 2, t = lane & 3;
     const int P1 = G1 * G1 * G1, NYB = (G1 + RBF - 1) / RBF;
     const int TL = (2 * RBF + 1) * G;
     // B fragments: k slot q of k-step s <-> tap 8s + q (taps 27..31 are zero padding); n = g <-> channel 8j + g
@@ -1334,6 +1355,8 @@ conv1_fwd_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const in
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[1])) : "memory");
+        mbar_init(&mbar_empty[0], C1M_WARPS);
+        mbar_init(&mbar_empty[1], C1M_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1356,29 +1379,47 @@ conv1_fwd_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const in
         for (int i = 0; i < 3; ++i)
             bulk_g2s(dst + (uint32_t)(i * TL * 4), orow + ((int64_t)(2 * x1 + i) * G + 2 * y0) * G, tri_bytes, bar);
     };
-    if (tid == 0 && rb0 < rb1) issue(rb0, 0);
-    uint32_t phase[2] = {0, 0};
+    const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&mbar[0]), empty0 = (uint32_t)__cvta_generic_to_shared(&mbar_empty[0]);
     bool ok = true;
-    for (int rb = rb0; rb < rb1; ++rb) {
-        const int stage = (rb - rb0) & 1;
-        if (tid == 0 && rb + 1 < rb1) issue(rb + 1, stage ^ 1);
-        ok = mbar_wait_parity((uint32_t)__cvta_generic_to_shared(&mbar[stage]), phase[stage]) && ok;
-        phase[stage] ^= 1;
-        int b, x1, y0, nr;
-        decode(rb, b, x1, y0, nr);
-        const float* ts = dsm + stage * 3 * TL;
-        const int64_t out_base = (int64_t)b * P1 + ((int64_t)x1 * G1 + y0) * G1;
-        float S1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, S2[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, cnt = 0.f;
-        const uint32_t inexact = conv1_mma_rowblock<false>(ts, G, G1, nr, out_base, y1, bh, bl, toff, bias_r, S1, S2, cnt);
-        if (__syncthreads_or((int)inexact)) {                        // block-uniform: some input value is not a TF32 number
+    // shifted sums (shift = bias) of this thread's outputs over ALL the block's row blocks: <= a few hundred values per slot
+    float S1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, S2[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, cnt = 0.f;
+    if (warp == C1M_WARPS) {                                         // ---- producer warp ----
+        if (lane == 0)
+            for (int rb = rb0; rb < rb1; ++rb) {
+                const int j = rb - rb0, stage = j & 1;
+                if (j >= 2) ok = mbar_wait_parity(empty0 + 8u * stage, (uint32_t)(((j >> 1) - 1) & 1)) && ok;
+                issue(rb, stage);
+            }
+        __syncwarp();
+    } else {
+        for (int rb = rb0; rb < rb1; ++rb) {
+            const int j = rb - rb0, stage = j & 1;
+            ok = mbar_wait_parity(full0 + 8u * stage, (uint32_t)((j >> 1) & 1)) && ok;
+            int b, x1, y0, nr;
+            decode(rb, b, x1, y0, nr);
+            const float* ts = dsm + stage * 3 * TL;
+            const int64_t out_base = (int64_t)b * P1 + ((int64_t)x1 * G1 + y0) * G1;
+            float K1[2][2], K2[2][2];
+            const float kcnt = cnt;
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                for (int e = 0; e < 2; ++e) { S1[j][e] = 0.f; S2[j][e] = 0.f; }
-            cnt = 0.f;
-            conv1_mma_rowblock<true>(ts, G, G1, nr, out_base, y1, bh, bl, toff, bias_r, S1, S2, cnt);
+                for (int e = 0; e < 2; ++e) { K1[jj][e] = S1[jj][e]; K2[jj][e] = S2[jj][e]; }
+            const uint32_t inexact = conv1_mma_rowblock<false>(ts, G, G1, nr, out_base, y1, bh, bl, toff, bias_r, S1, S2, cnt);
+            if (__any_sync(0xffffffffu, inexact != 0u)) {            // this warp met an input value that is not a TF32 number
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) { S1[jj][e] = K1[jj][e]; S2[jj][e] = K2[jj][e]; }
+                cnt = kcnt;
+                conv1_mma_rowblock<true>(ts, G, G1, nr, out_base, y1, bh, bl, toff, bias_r, S1, S2, cnt);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8u * stage);
         }
-        if (part) {                                                  // uniform
+    }
+    if (part) {                                                      // uniform: one (mean, M2, n) record per block
+        if (warp < C1M_WARPS) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -1400,17 +1441,16 @@ conv1_fwd_mma_kernel(const float* __restrict__ obs, int64_t obs_stride, const in
                         red[warp][c] = mean; red[warp][C1 + c] = M2; red[warp][2 * C1 + c] = n;
                     }
                 }
-            __syncthreads();
-            if (tid < C1) {
-                float n = 0.f, mean = 0.f, M2 = 0.f;
-#pragma unroll
-                for (int wv = 0; wv < C1M_WARPS; ++wv) chan_merge_f(n, mean, M2, red[wv][2 * C1 + tid], red[wv][tid], red[wv][C1 + tid]);
-                float* pr = part + (int64_t)rb * PART_STRIDE;
-                pr[tid] = mean; pr[C1 + tid] = M2;
-                if (tid == 0) pr[2 * C1] = n;
-            }
         }
-        __syncthreads();                                             // stage and red[] are free for the next row block
+        __syncthreads();
+        if (tid < C1) {
+            float n = 0.f, mean = 0.f, M2 = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < C1M_WARPS; ++wv) chan_merge_f(n, mean, M2, red[wv][2 * C1 + tid], red[wv][tid], red[wv][C1 + tid]);
+            float* pr = part + (int64_t)blockIdx.x * PART_STRIDE;
+            pr[tid] = mean; pr[C1 + tid] = M2;
+            if (tid == 0) pr[2 * C1] = n;
+        }
     }
     if (!ok) { asm volatile("trap;"); }
 }
@@ -1644,14 +1684,15 @@ int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, i
         const int rbpb = (int)std::max<int64_t>(1, ceil_div(total_rb, 1184));
         if (conv1_mma_mode() & 1) {
             { int rc_ = ensure_dyn_smem(conv1_fwd_mma_kernel, smem_c1); if (rc_) return rc_; }
-            conv1_fwd_mma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), C1M_THREADS, smem_c1, stream>>>(
+            conv1_fwd_mma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), C1F_THREADS, smem_c1, stream>>>(
                 obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
+            nrec1 = (int)ceil_div(total_rb, rbpb);                   // one BN record per block
         } else {
             { int rc_ = ensure_dyn_smem(conv1_fwd_tma_kernel, smem_c1); if (rc_) return rc_; }
             conv1_fwd_tma_kernel<<<(unsigned)ceil_div(total_rb, rbpb), CONV1_THREADS, smem_c1, stream>>>(
                 obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b, ws + w.y1, part1, d.G, d.G1, d.rbf1, total_rb, rbpb);
+            nrec1 = total_rb;
         }
-        nrec1 = total_rb;
     } else {
         conv1_fwd_kernel<<<dim3(d.nblk1, B), CONV1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, p->conv1_w, p->conv1_b,
                                                                           ws + w.y1, part1, d.G, d.G1);
@@ -1888,7 +1929,7 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
             const int nblk_m = (int)ceil_div(total_m, rbpb_m);
             const size_t smem_m = (size_t)2 * (3 * (2 * WG1M_RB + 1) * d.G + 2 * WG1M_RB * d.G1 * C1) * 4;
             { int rc_ = ensure_dyn_smem(conv1_wgrad_mma_kernel<WG1M_RB>, smem_m); if (rc_) return rc_; }
-            conv1_wgrad_mma_kernel<WG1M_RB><<<nblk_m, C1M_THREADS, smem_m, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1,
+            conv1_wgrad_mma_kernel<WG1M_RB><<<nblk_m, WG1M_THREADS, smem_m, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1,
                                                                                      ws + w.y1, ws + w.stat1, ws + w.coef1, ws + w.wg1part,
                                                                                      d.G, d.G1, total_m, rbpb_m);
             nblk = nblk_m;

@@ -13,6 +13,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {          // one (release) arrival, e.g. "this warp is done with the stage"
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
 __device__ __forceinline__ bool mbar_wait_parity(uint32_t mbar, uint32_t parity) {
     for (uint32_t it = 0; it < (1u << 26); ++it) {          // bounded: a lost copy must not hang the GPU
         uint32_t ok;
