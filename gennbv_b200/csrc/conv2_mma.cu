@@ -663,24 +663,27 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
             if (warp == 0) { db_lo += a0 + a2; db_hi += a1 + a3; }
             uint32_t ah[4], al[4];
             split_tf32(a0, ah[0], al[0]); split_tf32(a1, ah[1], al[1]); split_tf32(a2, ah[2], al[2]); split_tf32(a3, ah[3], al[3]);
+            // B (k = position, n = ci): b0 = x[row t, 2*za + l][ci], b1 = x[row t, 2*zb + l][ci] for the warp's three n-tiles, then
+            // the nine MMAs issued tile-interleaved: the three products of one accumulator (lo*hi, hi*lo, hi*hi, in this order)
+            // are a dependent chain, and back to back they left the tensor pipe waiting on its own result (NOP + stall_wait
+            // after every HMMA in the round-2 profile).
+            // (precomputing the per-n-tile line offsets once per kernel was measured no faster: 3.41 vs 3.33 ms/step)
+            uint32_t bh0[WGS_NT], bl0[WGS_NT], bh1[WGS_NT], bl1[WGS_NT];
 #pragma unroll
             for (int k = 0; k < WGS_NT; ++k) {
-                const int nt = warp + WGS_WARPS * k;
-                if (nt < 2 * NTAPS) {                       // warp-uniform
-                    // B (k = position, n = ci): b0 = x[row t, 2*za + l][ci], b1 = x[row t, 2*zb + l][ci]
-                    // (precomputing the per-n-tile line offsets once per kernel was measured no faster: 3.41 vs 3.33 ms/step)
-                    const int tap = nt >> 1;
-                    const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
-                    const float* line = xs + (i * 9 + 2 * tc + jy) * LP + l * C + 8 * hf + g;
-                    const float x0 = fmaxf(fmaf(scv, line[2 * za * C], shv), 0.f);
-                    const float x1 = fmaxf(fmaf(scv, line[2 * zbc * C], shv), 0.f);
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(x0, bh0, bl0); split_tf32(x1, bh1, bl1);
-                    mma_tf32(acc[k], al[0], al[1], al[2], al[3], bh0, bh1);
-                    mma_tf32(acc[k], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
-                    mma_tf32(acc[k], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
-                }
+                const int tap = (warp + WGS_WARPS * k) >> 1;
+                const int i = tap / 9, r9 = tap - 9 * i, jy = r9 / 3, l = r9 - 3 * jy;
+                const float* line = xs + (i * 9 + 2 * tc + jy) * LP + l * C + 8 * hf + g;
+                const float x0 = fmaxf(fmaf(scv, line[2 * za * C], shv), 0.f);
+                const float x1 = fmaxf(fmaf(scv, line[2 * zbc * C], shv), 0.f);
+                split_tf32(x0, bh0[k], bl0[k]); split_tf32(x1, bh1[k], bl1[k]);
             }
+#pragma unroll
+            for (int k = 0; k < WGS_NT; ++k) mma_tf32(acc[k], al[0], al[1], al[2], al[3], bh0[k], bh1[k]);
+#pragma unroll
+            for (int k = 0; k < WGS_NT; ++k) mma_tf32(acc[k], ah[0], ah[1], ah[2], ah[3], bl0[k], bl1[k]);
+#pragma unroll
+            for (int k = 0; k < WGS_NT; ++k) mma_tf32(acc[k], ah[0], ah[1], ah[2], ah[3], bh0[k], bh1[k]);
         }
 #pragma unroll
         for (int k = 0; k < WGS_NT; ++k) { tot[k][0] += acc[k][0]; tot[k][1] += acc[k][1]; tot[k][2] += acc[k][2]; tot[k][3] += acc[k][3]; }
@@ -691,14 +694,11 @@ conv2_wgrad_staged_kernel(const float* __restrict__ y1, const float* __restrict_
     float* out = part + (int64_t)blockIdx.x * WG_REC;
 #pragma unroll
     for (int k = 0; k < WGS_NT; ++k) {
-        const int nt = warp + WGS_WARPS * k;
-        if (nt < 2 * NTAPS) {
-            const int tap = nt >> 1;
+        const int tap = (warp + WGS_WARPS * k) >> 1;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int co = g + 8 * (e >> 1), ci = 8 * hf + 2 * t + (e & 1);
-                out[(co * C + ci) * NTAPS + tap] = tot[k][e];
-            }
+        for (int e = 0; e < 4; ++e) {
+            const int co = g + 8 * (e >> 1), ci = 8 * hf + 2 * t + (e & 1);
+            out[(co * C + ci) * NTAPS + tap] = tot[k][e];
         }
     }
     if (warp == 0) {

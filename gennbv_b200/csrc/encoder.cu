@@ -1088,21 +1088,28 @@ __device__ __forceinline__ uint32_t conv1_wgrad_mma_rowblock(const float* __rest
         // B (k = position, n = tap 8j + g): input voxel (2r + jj, 2z + l) of slab i
         const float* pa = ts + (2 * r) * G + 2 * zac;
         const float* pb = ts + (2 * r) * G + 2 * zbc;
+        if (SPLIT_B) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float x0 = pa[boff[j]], x1 = pb[boff[j]];
-            if (SPLIT_B) {
+            for (int j = 0; j < 4; ++j) {
+                const float x0 = pa[boff[j]], x1 = pb[boff[j]];
                 uint32_t h0, l0, h1, l1;
                 split_tf32(x0, h0, l0); split_tf32(x1, h1, l1);
                 mma_tf32(acc[j], al[0], al[1], al[2], al[3], h0, h1);
                 mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], l0, l1);
                 mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], h0, h1);
-            } else {
-                const uint32_t b0 = __float_as_uint(x0), b1 = __float_as_uint(x1);
-                orbits |= b0 | b1;
-                mma_tf32(acc[j], al[0], al[1], al[2], al[3], b0, b1);
-                mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], b0, b1);
             }
+        } else {
+            // the two products of one accumulator are a dependent chain: issue the four n-tiles interleaved
+            uint32_t b0[4], b1[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                b0[j] = __float_as_uint(pa[boff[j]]); b1[j] = __float_as_uint(pb[boff[j]]);
+                orbits |= b0[j] | b1[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_tf32(acc[j], al[0], al[1], al[2], al[3], b0[j], b1[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_tf32(acc[j], ah[0], ah[1], ah[2], ah[3], b0[j], b1[j]);
         }
     }
     return orbits & 0x1fffu;
