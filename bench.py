@@ -452,7 +452,14 @@ def run_native(args, rank, world):
                       "frac_of_binding_roofline": max(t_hbm, t_tc) / ms}
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     dk = kernels[dom]
-    traffic = None                                               # ncu dram__bytes per launch: see profiles/ (r02 captures)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from ONE `ncu --set full` capture of this command at the default
+    # workload (profiles/r02z_ncu_full_step.txt; a property of the kernel and the shapes, not of this run's timing)
+    ncu_dram_mb = {"scan_raycast": 33.7, "grid_update+coverage": 640.7, "fwd.conv1": 718.6, "fwd.conv2": 545.5, "fwd.grid_fc": 116.7,
+                   "bwd.grid_fc": 158.4, "bwd.conv2_wgrad": 557.9, "bwd.conv2_dgrad": 1034.3, "bwd.conv1_wgrad": 1263.9}
+    default_shape = (N, G, P) == (256, 64, 128 * 128) and grid_sparse
+    for k in kernels:
+        kernels[k]["ncu_dram_mb"] = ncu_dram_mb.get(k) if default_shape else None
+    traffic = ncu_dram_mb[dom] * 1e6 if default_shape and dom in ncu_dram_mb else None
     if dk["bound"] == "hbm":
         roofline = {"bound": "hbm", "kernel": dom, "achieved": dk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dk["frac_hbm"],
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": work[dom][0]}
@@ -473,7 +480,8 @@ def run_native(args, rank, world):
         "stages_ms": stages, "step_ms_spread": step_spread, "encoder_kernel_ms": kernel_ms,
         "roofline": roofline,
         "roofline_hbm": {"bound": "hbm", "kernel": "grid_update_sparse_kernel" if grid_sparse else "grid_update_kernel",
-                         "achieved": gk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": gk["frac_hbm"], "traffic": None, "ms": gk["ms"],
+                         "achieved": gk["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": gk["frac_hbm"],
+                         "traffic": ncu_dram_mb["grid_update+coverage"] * 1e6 if default_shape else None, "ms": gk["ms"],
                          "bytes_moved_per_launch": work["grid_update+coverage"][0],
                          "dense_algorithmic_bytes_per_launch": N * (V * 24 + 4),
                          "speedup_vs_dense_figure": N * (V * 24 + 4) / work["grid_update+coverage"][0],

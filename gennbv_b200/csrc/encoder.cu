@@ -306,10 +306,21 @@ conv2_fwd_kernel(const float* __restrict__ y1, const float* __restrict__ stat1, 
 // act2 = relu(a2[c] * y2 + b2[c]), [B,16,P2] channel-major
 __global__ void bn_relu_apply_kernel(const float* __restrict__ y2, const float* __restrict__ stat2, float* __restrict__ act2,
                                      int64_t total, int P2) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // four consecutive elements per thread (the flat [B,16,P2] array is 16-byte aligned and total % 4 == 0 -- 16 * P2 per sample);
+    // the channel can change inside a quad only at a row end
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, idx = 4 * q;
     if (idx >= total) return;
-    int c = (int)((idx / P2) % C1);
-    act2[idx] = fmaxf(fmaf(stat2[2 * C1 + c], y2[idx], stat2[3 * C1 + c]), 0.f);
+    const float4 v = *reinterpret_cast<const float4*>(y2 + idx);
+    const int64_t row = idx / P2;
+    const int rem = (int)(idx - row * P2);
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float out[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = (int)((row + (rem + e >= P2 ? 1 : 0)) % C1);
+        out[e] = fmaxf(fmaf(stat2[2 * C1 + c], in[e], stat2[3 * C1 + c]), 0.f);
+    }
+    *reinterpret_cast<float4*>(act2 + idx) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 
@@ -327,13 +338,25 @@ __global__ void relu_mask_kernel(const float* __restrict__ dy_in, int64_t ldi, f
 }
 
 // db[j] = sum_i dy[i,j]  (rows summed in order: deterministic)
-__global__ void colsum_kernel(const float* __restrict__ dy, int64_t ld, int rows, int cols, float* __restrict__ db) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= cols) return;
-    float s = 0.f;
-    for (int i = 0; i < rows; ++i) s += dy[(int64_t)i * ld + j];
-    db[j] = s;
+// column sums of a [rows, cols] matrix (row stride ld): 32 columns x 8 interleaved row slices per block, the slices combined in a
+// fixed order (deterministic), accumulation in double.  Launch with colsum_blocks(cols) blocks of 256 threads.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ dy, int64_t ld, int rows, int cols, float* __restrict__ db) {
+    __shared__ double sh[8][33];
+    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5, j = blockIdx.x * 32 + cx;
+    double s = 0.0;
+    if (j < cols)
+        for (int i = sy; i < rows; i += 8) s += (double)dy[(int64_t)i * ld + j];
+    sh[sy][cx] = s;
+    __syncthreads();
+    if (sy == 0 && j < cols) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][cx];
+        db[j] = (float)t;
+    }
 }
+static inline unsigned colsum_blocks(int cols) { return (unsigned)((cols + 31) / 32); }
 
 // BN2 backward, pass 1: per (sample, channel) sums of g = dact2 * [act2 > 0] and g * xhat.  part [B][16][2]
 __global__ void __launch_bounds__(256)
@@ -342,12 +365,14 @@ bn2_bwd_reduce_kernel(const float* __restrict__ dact2, const float* __restrict__
     __shared__ float sh[2][8];
     const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int64_t base = ((int64_t)b * C1 + c) * P2;
-    const float mean = stat2[c], invstd = stat2[C1 + c];
+    const float mean = stat2[c], invstd = stat2[C1 + c], sc = stat2[2 * C1 + c], sh_ = stat2[3 * C1 + c];
     float s1 = 0.f, s2 = 0.f;
+    (void)act2;     // the ReLU mask is recomputed from y2 with the forward's own expression (bn_relu_apply_kernel): 55 MB less to read
     for (int p = tid; p < P2; p += 256) {
-        float g = act2[base + p] > 0.f ? dact2[base + p] : 0.f;
+        const float yv = y2[base + p];
+        float g = fmaf(sc, yv, sh_) > 0.f ? dact2[base + p] : 0.f;
         s1 += g;
-        s2 = fmaf(g, (y2[base + p] - mean) * invstd, s2);
+        s2 = fmaf(g, (yv - mean) * invstd, s2);
     }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
     if ((tid & 31) == 0) { sh[0][tid >> 5] = s1; sh[1][tid >> 5] = s2; }
@@ -391,8 +416,9 @@ bn2_bwd_apply_kernel(const float* __restrict__ dact2, const float* __restrict__ 
 #pragma unroll
     for (int c = 0; c < C1; ++c) {
         const int64_t i = ((int64_t)b * C1 + c) * P2 + p;
-        const float g = act2[i] > 0.f ? dact2[i] : 0.f;
-        const float xhat = (y2[i] - stat2[c]) * stat2[C1 + c];
+        const float yv = y2[i];
+        const float g = fmaf(stat2[2 * C1 + c], yv, stat2[3 * C1 + c]) > 0.f ? dact2[i] : 0.f;   // same mask as act2 > 0
+        const float xhat = (yv - stat2[c]) * stat2[C1 + c];
         out[c] = stat2[2 * C1 + c] * (g - coef[c] - xhat * coef[C1 + c]);
     }
     float4* o = reinterpret_cast<float4*>(dy2cl + ((int64_t)b * P2 + p) * C1);
@@ -534,12 +560,23 @@ conv2_wgrad_kernel(const float* __restrict__ y1, const float* __restrict__ stat1
 __global__ void __launch_bounds__(256)
 reduce_records_kernel(const float* __restrict__ part, int nrec, int rec, float* __restrict__ out_a, int na,
                       float* __restrict__ out_b) {
-    const int j = blockIdx.x * 256 + threadIdx.x;
-    if (j >= rec) return;
+    // 32 record columns x 8 interleaved record slices per block, slices combined in a fixed order (deterministic), double
+    // accumulation; launch with (rec + 31) / 32 blocks of 256 threads.  (One thread per column walking all the records serially
+    // took 52 us per call for 148 x 6928 / 1176 x 448 floats.)
+    __shared__ double sh[8][33];
+    const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5, j = blockIdx.x * 32 + cx;
     double s = 0.0;
-    for (int k = 0; k < nrec; ++k) s += (double)part[(int64_t)k * rec + j];
-    if (j < na) out_a[j] = (float)s;
-    else out_b[j - na] = (float)s;
+    if (j < rec)
+        for (int k = sy; k < nrec; k += 8) s += (double)part[(int64_t)k * rec + j];
+    sh[sy][cx] = s;
+    __syncthreads();
+    if (sy == 0 && j < rec) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sh[k][cx];
+        if (j < na) out_a[j] = (float)t;
+        else out_b[j - na] = (float)t;
+    }
 }
 
 // conv2 data gradient + ReLU/BN1 backward statistics.
@@ -1755,7 +1792,7 @@ int gnbv::encoder_forward_impl(const gnbv_encoder_params* p, const float* obs, i
         bn_eval_affine_kernel<<<1, 32, 0, stream>>>(p->bn2_w, p->bn2_b, p->bn2_rm, p->bn2_rv, ws + w.stat2, 1e-5f);
     GNBV_LAUNCH_CHECK("bn2 statistics");
     const int64_t tot2 = (int64_t)B * d.flat2;
-    bn_relu_apply_kernel<<<(unsigned)ceil_div(tot2, 256), 256, 0, stream>>>(ws + w.y2, ws + w.stat2, ws + w.act2, tot2, d.P2);
+    bn_relu_apply_kernel<<<(unsigned)ceil_div(tot2 / 4, 256), 256, 0, stream>>>(ws + w.y2, ws + w.stat2, ws + w.act2, tot2, d.P2);
     GNBV_LAUNCH_CHECK("bn_relu_apply_kernel");
     // Linear(16*G2^3, 256)+ReLU -> cat[:, 256:512]
     stage_mark(GNBV_ST_FWD_GRID_FC, stream);
@@ -1829,26 +1866,26 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
     GNBV_LAUNCH_CHECK("relu_mask_kernel");
     rc = launch_gemm(ws + w.dz, 1, d.FEAT, ws + w.cat, CAT, 1, gr->out_fc_w, CAT, d.FEAT, CAT, B, none, ws + w.gemm, stream);
     if (rc) return rc;
-    colsum_kernel<<<blocks(d.FEAT), 256, 0, stream>>>(ws + w.dz, d.FEAT, B, d.FEAT, gr->out_fc_b);
+    colsum_kernel<<<colsum_blocks(d.FEAT), 256, 0, stream>>>(ws + w.dz, d.FEAT, B, d.FEAT, gr->out_fc_b);
     rc = launch_gemm(ws + w.dz, d.FEAT, 1, p->out_fc_w, CAT, 1, ws + w.dcat, CAT, B, CAT, d.FEAT, none, ws + w.gemm, stream);
     if (rc) return rc;
     relu_mask_kernel<<<blocks((int64_t)B * CAT), 256, 0, stream>>>(ws + w.dcat, CAT, ws + w.dcat, CAT, ws + w.cat, CAT, B, CAT);
     // ---- action branch
     rc = launch_gemm(ws + w.dcat, 1, CAT, ws + w.h1, H, 1, gr->act_fc2_w, H, H, H, B, none, ws + w.gemm, stream);
     if (rc) return rc;
-    colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dcat, CAT, B, H, gr->act_fc2_b);
+    colsum_kernel<<<colsum_blocks(H), 256, 0, stream>>>(ws + w.dcat, CAT, B, H, gr->act_fc2_b);
     rc = launch_gemm(ws + w.dcat, CAT, 1, p->act_fc2_w, H, 1, ws + w.dh1, H, B, H, H, none, ws + w.gemm, stream);
     if (rc) return rc;
     relu_mask_kernel<<<blocks((int64_t)B * H), 256, 0, stream>>>(ws + w.dh1, H, ws + w.dh1, H, ws + w.h1, H, B, H);
     rc = launch_gemm(ws + w.dh1, 1, H, ws + w.pe, 4 * d.S, 1, gr->act_fc1_w, 4 * d.S, H, 4 * d.S, B, none, ws + w.gemm, stream);
     if (rc) return rc;
-    colsum_kernel<<<blocks(H), 256, 0, stream>>>(ws + w.dh1, H, B, H, gr->act_fc1_b);
+    colsum_kernel<<<colsum_blocks(H), 256, 0, stream>>>(ws + w.dh1, H, B, H, gr->act_fc1_b);
     // ---- grid branch: Linear
     stage_mark(GNBV_ST_BWD_GRID_FC, stream);
     const float* dcat_g = ws + w.dcat + H;
     rc = launch_gemm(dcat_g, 1, CAT, ws + w.act2, d.flat2, 1, gr->grid_fc_w, d.flat2, H, (int)d.flat2, B, none, ws + w.gemm, stream);
     if (rc) return rc;
-    colsum_kernel<<<blocks(H), 256, 0, stream>>>(dcat_g, CAT, B, H, gr->grid_fc_b);
+    colsum_kernel<<<colsum_blocks(H), 256, 0, stream>>>(dcat_g, CAT, B, H, gr->grid_fc_b);
     rc = launch_gemm(dcat_g, CAT, 1, p->grid_fc_w, d.flat2, 1, ws + w.dact2, d.flat2, B, (int)d.flat2, H, none, ws + w.gemm, stream);
     if (rc) return rc;
     if (sem) {
@@ -1857,7 +1894,7 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
         const int FS = sem2d_flat();
         rc = launch_gemm(dcat_s, 1, CAT, ws + w.s_out2, FS, 1, gr->rgb_fc_w, FS, H, FS, B, none, ws + w.gemm, stream);
         if (rc) return rc;
-        colsum_kernel<<<blocks(H), 256, 0, stream>>>(dcat_s, CAT, B, H, gr->rgb_fc_b);
+        colsum_kernel<<<colsum_blocks(H), 256, 0, stream>>>(dcat_s, CAT, B, H, gr->rgb_fc_b);
         rc = launch_gemm(dcat_s, CAT, 1, p->rgb_fc_w, FS, 1, ws + w.s_dflat, FS, B, FS, H, none, ws + w.gemm, stream);
         if (rc) return rc;
         const int64_t rgb_off = (int64_t)state_dim + (int64_t)d.G * d.G * d.G;
@@ -1895,7 +1932,7 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
                                                                            d.G2, B * d.G2 * d.G2, w.wg2_pps);
     }
     GNBV_LAUNCH_CHECK("conv2_wgrad_kernel");
-    reduce_records_kernel<<<blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, nrec_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
+    reduce_records_kernel<<<colsum_blocks(WG2_REC), 256, 0, stream>>>(ws + w.wg2part, nrec_wg2, WG2_REC, gr->conv2_w, C1 * C1 * TAPS,
                                                                 gr->conv2_b);
     stage_mark(GNBV_ST_BWD_CONV2_DGRAD, stream);
     int nrec_dg;
@@ -1945,7 +1982,7 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
                                                                         ws + w.stat1, ws + w.coef1, ws + w.wg1part, d.G, d.G1,
                                                                         total_rb, rbpb);
         GNBV_LAUNCH_CHECK("conv1_wgrad_tma_kernel");
-        reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, nblk, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
+        reduce_records_kernel<<<colsum_blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, nblk, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
         GNBV_LAUNCH_CHECK("reduce_records_kernel");
         stage_mark(GNBV_ST_BWD_END, stream);
         return GNBV_OK;
@@ -1953,7 +1990,7 @@ extern "C" int gnbv_encoder_backward_phase(const gnbv_encoder_params* p, const f
     conv1_wgrad_kernel<<<w.nblk_wg1, WG1_THREADS, 0, stream>>>(obs, obs_row_stride, row_index, state_dim, ws + w.g1, ws + w.y1, ws + w.stat1,
                                                                 ws + w.coef1, ws + w.wg1part, d.G, d.G1, w.wg1_items, w.wg1_ips, vec1);
     GNBV_LAUNCH_CHECK("conv1_wgrad_kernel");
-    reduce_records_kernel<<<blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, w.nblk_wg1, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
+    reduce_records_kernel<<<colsum_blocks(WG1_REC), 256, 0, stream>>>(ws + w.wg1part, w.nblk_wg1, WG1_REC, gr->conv1_w, C1 * TAPS, gr->conv1_b);
     GNBV_LAUNCH_CHECK("reduce_records_kernel");
     stage_mark(GNBV_ST_BWD_END, stream);
     return GNBV_OK;

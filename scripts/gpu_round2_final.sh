@@ -17,5 +17,6 @@ timeout 400 ncu --nvtx --nvtx-include "timed/" --set full --clock-control none -
     -k regex:"scan_raycast|grid_update_sparse|conv1_fwd_mma|conv2_fwd_mma|tc_gemm|wgrad_staged|conv2_dgrad_mma|conv1_wgrad_mma" -c 10 \
     -o $OUT/prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ppo > $OUT/ncu_full.log 2>&1
 tail -2 $OUT/ncu_full.log | cut -c1-200
+echo "== tcgen05 micro-benchmarks"; (timeout 60 ./scripts/micro/mma_rate; timeout 60 ./scripts/micro/handoff_latency) > $OUT/micro_tcgen05.txt 2>&1; tail -4 $OUT/micro_tcgen05.txt
 echo "== chamfer stress"; timeout 150 python scripts/chamfer_stress.py --out $OUT/chamfer_stress.json 2>&1 | tail -1 | cut -c1-300
 ls -la $OUT
