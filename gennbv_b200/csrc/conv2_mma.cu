@@ -377,8 +377,21 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
                 }
             }
         };
+        // The epilogue needs y1 at the item's output voxels (streamed from HBM).  Its 16 loads ride in whichever tap buffer is
+        // idle during the LAST tap's MMAs -- same register footprint, and the round trip is over when the epilogue starts
+        // (issued after the loop they were 12 % of this kernel's stall samples).
+        float4 raw_a[MT][2], raw_b[MT][2];
+        auto load_y = [&](float4 (&buf)[MT][2]) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float* yp = y1 + ((int64_t)b * P1 + max(dst[m][h], 0)) * C + 2 * t;
+                    const float2 lo2 = __ldg(reinterpret_cast<const float2*>(yp)), hi2 = __ldg(reinterpret_cast<const float2*>(yp + 8));
+                    buf[m][h] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                }
+        };
         {
-            float4 raw_a[MT][2], raw_b[MT][2];
             int tap0, d0, tap1 = 0, d1 = 0;
             uint32_t n0, n1 = 0;
             tap_of(0, tap0, d0, n0);
@@ -386,16 +399,23 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
             for (int k = 0; k < ntap; k += 2) {                   // all conditions are block-uniform
                 const bool has1 = k + 1 < ntap;
                 if (has1) { tap_of(k + 1, tap1, d1, n1); load(raw_b, d1, n1); }
+                else load_y(raw_b);                               // single-tap class
                 compute(raw_a, tap0);
                 if (has1) {
                     if (k + 2 < ntap) { tap_of(k + 2, tap0, d0, n0); load(raw_a, d0, n0); }
+                    else load_y(raw_a);                           // last pair of taps
                     compute(raw_b, tap1);
                 }
             }
+            if (ntap == 1) {
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) raw_a[m][h] = raw_b[m][h];
+            }
         }
 
-        // ---- epilogue: ReLU mask from bn1(y1), store g1 (channels-last), BN1-backward partial sums.
-        // All 16 y1 loads of the thread are issued before the first use: one exposed memory latency instead of eight.
+        // ---- epilogue: ReLU mask from bn1(y1) (values already in raw_a), store g1 (channels-last), BN1-backward partial sums.
         float s1[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, s2[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
         float k_mean[2][2], k_istd[2][2], k_a[2][2], k_b[2][2];     // BN1 constants of the thread's channels c = 8j + 2t + e
 #pragma unroll
@@ -406,15 +426,6 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
                 k_mean[j][e] = __ldg(stat1 + c); k_istd[j][e] = __ldg(stat1 + C + c);
                 k_a[j][e] = __ldg(stat1 + 2 * C + c); k_b[j][e] = __ldg(stat1 + 3 * C + c);
             }
-        float2 yv[MT][2][2];
-#pragma unroll
-        for (int m = 0; m < MT; ++m)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int64_t base = ((int64_t)b * P1 + max(dst[m][h], 0)) * C;
-#pragma unroll
-                for (int j = 0; j < 2; ++j) yv[m][h][j] = __ldg(reinterpret_cast<const float2*>(y1 + base + 8 * j + 2 * t));
-            }
 #pragma unroll
         for (int m = 0; m < MT; ++m)
 #pragma unroll
@@ -423,7 +434,7 @@ conv2_dgrad_mma_kernel(const float* __restrict__ dy2cl, const float* __restrict_
                 const int64_t base = ((int64_t)b * P1 + dst[m][h]) * C;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const float y2v[2] = {yv[m][h][j].x, yv[m][h][j].y};
+                    const float y2v[2] = {j ? raw_a[m][h].z : raw_a[m][h].x, j ? raw_a[m][h].w : raw_a[m][h].y};
                     float o[2];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
