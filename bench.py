@@ -453,9 +453,9 @@ def run_native(args, rank, world):
     dom = max(kernels, key=lambda k: kernels[k]["ms"])
     dk = kernels[dom]
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from ONE `ncu --set full` capture of this command at the default
-    # workload (profiles/r02z_ncu_full_step.txt; a property of the kernel and the shapes, not of this run's timing)
+    # workload (profiles/r02g_ncu_full_step.txt; a property of the kernel and the shapes, not of this run's timing)
     ncu_dram_mb = {"scan_raycast": 33.7, "grid_update+coverage": 640.7, "fwd.conv1": 718.6, "fwd.conv2": 545.5, "fwd.grid_fc": 116.7,
-                   "bwd.grid_fc": 158.4, "bwd.conv2_wgrad": 557.9, "bwd.conv2_dgrad": 1034.3, "bwd.conv1_wgrad": 1263.9}
+                   "bwd.grid_fc": 158.4, "bwd.conv2_wgrad": 557.9, "bwd.conv2_dgrad": 1078.5, "bwd.conv1_wgrad": 1263.9}
     default_shape = (N, G, P) == (256, 64, 128 * 128) and grid_sparse
     for k in kernels:
         kernels[k]["ncu_dram_mb"] = ncu_dram_mb.get(k) if default_shape else None
