@@ -167,7 +167,7 @@ def run_reference(args, rank):
     sample = (f"{n} of {ENVS_PER_GPU} envs per step, {args.steps} steps; PyTorch-CPU restatement of the reference's "
               f"update_occ_grid path (oracle/torch_ref.py) + reference encoder fwd/bwd (oracle/encoder_ref.py), "
               f"{threads} torch threads")
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3 * ENVS_PER_GPU / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -175,7 +175,7 @@ def run_reference(args, rank):
         "stages_ms_per_sample_step": {k: v * 1e3 for k, v in stages.items()},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -507,9 +507,20 @@ def run_native(args, rank, world):
                                "sample": f"{n} of {N} envs x 2 steps; PyTorch-CPU restatement of the reference path "
                                          f"(oracle/torch_ref.py + oracle/encoder_ref.py), stages s/step: "
                                          + ", ".join(f"{k} {v:.2f}" for k, v in st.items())}
-    print(json.dumps(out))
+    _emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+_STDOUT_FD = None
+
+
+def _emit(record):
+    """Print the one JSON line on the real stdout (see main())."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(record), flush=True)
 
 
 def main():
@@ -527,6 +538,12 @@ def main():
     ap.add_argument("--ppo-steps", type=int, default=128, help="n_steps of the PPO iteration record (reference default 128)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    # stdout carries exactly ONE line, the JSON record: until it is printed, file descriptor 1 points at stderr, so that
+    # anything a library writes to stdout on the way (NCCL's version banner at the first collective) cannot precede it
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
