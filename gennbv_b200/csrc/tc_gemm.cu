@@ -15,7 +15,6 @@
 namespace gnbv {
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 256;
 
 struct TcGemmArgs {
     const float* A; int64_t sa_m, sa_k;
@@ -28,68 +27,19 @@ struct TcGemmArgs {
     int* err;
 };
 
-// Stage an [R x BK] operand tile (rows r0.., K range k0..) into smem as (hi, lo) K-major tiles.
+// Operand staging: an [R x BK] tile (rows r0.., K range k0..) goes to shared memory as (hi, lo) K-major UMMA tiles.
 // MODE 0: K contiguous in global (element (r,k) at base[r*ld_r + k]); MODE 1: rows contiguous (base[r + k*ld_k]).
-template <int R, int MODE>
-__device__ __forceinline__ void stage_tile(const float* __restrict__ base, int64_t ld, int r0, int rows, int k0, int k_end,
-                                           bool vec, uint8_t* hi, uint8_t* lo) {
-    const int t = threadIdx.x;
-    if (MODE == 0) {
-        for (int u = t; u < R * (tc::BK / 4); u += TC_THREADS) {
-            const int r_low = u & 7, k4 = (u >> 3) & 7, r = (u >> 6) * 8 + r_low;
-            const int gr = r0 + r, gk = k0 + k4 * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gr < rows) {
-                const float* p = base + (int64_t)gr * ld + gk;
-                if (vec && gk + 3 < k_end) v = __ldg(reinterpret_cast<const float4*>(p));
-                else {
-                    if (gk < k_end) v.x = __ldg(p);
-                    if (gk + 1 < k_end) v.y = __ldg(p + 1);
-                    if (gk + 2 < k_end) v.z = __ldg(p + 2);
-                    if (gk + 3 < k_end) v.w = __ldg(p + 3);
-                }
-            }
-            float4 h, l;
-            tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
-            const uint32_t off = tc::tile_offset(r, k4 * 4);
-            *reinterpret_cast<float4*>(hi + off) = h;
-            *reinterpret_cast<float4*>(lo + off) = l;
-        }
-    } else {
-        for (int u = t; u < (R / 4) * tc::BK; u += TC_THREADS) {
-            const int r4 = u % (R / 4), k = u / (R / 4);
-            const int gr = r0 + r4 * 4, gk = k0 + k;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gk < k_end) {
-                const float* p = base + (int64_t)gk * ld + gr;
-                if (vec && gr + 3 < rows) v = __ldg(reinterpret_cast<const float4*>(p));
-                else {
-                    if (gr < rows) v.x = __ldg(p);
-                    if (gr + 1 < rows) v.y = __ldg(p + 1);
-                    if (gr + 2 < rows) v.z = __ldg(p + 2);
-                    if (gr + 3 < rows) v.w = __ldg(p + 3);
-                }
-            }
-            const float x[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float h, l;
-                tc::split_tf32(x[e], h, l);
-                const uint32_t off = tc::tile_offset(r4 * 4 + e, k);
-                *reinterpret_cast<float*>(hi + off) = h;
-                *reinterpret_cast<float*>(lo + off) = l;
-            }
-        }
-    }
-}
 
 // ---- warp-specialised pipeline --------------------------------------------------------------------------------------
-// warps 0-7  producers: per K stage (BK = 32) request the stage's A and B elements from global memory into REGISTERS first
-//            (12 x 16 B per thread in flight, issued before the shared-memory slot is known to be free), then wait for the
-//            slot, split every value into (hi, lo) and store both into the canonical K-major UMMA layout; one mbarrier
-//            arrival per warp.  After the K loop the same warps are the epilogue (TMEM -> registers -> global).
-// warp 8     one elected thread issues the 12 tcgen05.mma of a stage (3xTF32) and tcgen05.commit's the slot back.
-// The loads of stage s+1 and the split / store of stage s overlap the MMAs of the stages before them.
+// warps 0-7   producers: per K stage (BK = 32) request the stage's A and B elements from global memory into REGISTERS first
+//             (12 x 16 B per thread in flight, issued before the shared-memory slot is known to be free), then wait for the
+//             slot, split every value into (hi, lo) and store both into the canonical K-major UMMA layout; one mbarrier
+//             arrival per warp.
+// warp 8      one elected thread issues the 12 tcgen05.mma of a stage (3xTF32) and tcgen05.commit's the slot back.
+// warps 9-12  epilogue: TMEM -> registers -> shared-memory transpose -> coalesced global stores, on the accumulator buffer the MMA
+//             warp is not writing (two TMEM accumulators of BN columns each).
+// The loads of stage s+1 overlap the MMAs of stage s; the load latency of a stage itself is exposed to the producers (DESIGN.md
+// section 10, item 1).
 constexpr int WS_PROD = 256, WS_EPI = 128, WS_THREADS = WS_PROD + 32 + WS_EPI;
 
 template <int R>
