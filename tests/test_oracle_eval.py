@@ -66,3 +66,17 @@ def test_rounding_is_half_even_in_fp32_and_rows_come_out_sorted():
     want = torch.unique(torch.round(torch.from_numpy(p), decimals=2), dim=0).numpy()
     np.testing.assert_array_equal(r, want)
     assert r.shape[0] == 3
+
+
+def test_chamfer_oracle_equals_the_brute_force_definition():
+    """pytorch3d.loss.chamfer_distance defaults (norm 2, point_reduction "mean", single cloud pair): mean over x of the squared
+    distance to the nearest y, plus the same with the roles swapped.  The oracle's k-d tree evaluation against all P1 x P2 pairs."""
+    rng = np.random.default_rng(7)
+    for p1, p2 in ((1, 1), (17, 5), (300, 411)):
+        x = rng.normal(size=(p1, 3)).astype(np.float32)
+        y = (rng.normal(size=(p2, 3)) * 1.5 + 0.3).astype(np.float32)
+        d2 = ((x[:, None, :].astype(np.float64) - y[None, :, :].astype(np.float64)) ** 2).sum(-1)
+        want = d2.min(1).mean() + d2.min(0).mean()
+        got = c_oracle.chamfer(x, y)
+        got = float(got[0] + got[1]) if isinstance(got, (tuple, list)) else float(got)
+        assert abs(got - want) <= 1e-12 * max(1.0, want), (p1, p2, got, want)
